@@ -1,0 +1,285 @@
+"""ctypes binding of libfaucet_gpu.so (include/faucet_gpu.h).  Fails loudly if the library is missing."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfaucet_gpu.so")
+
+
+class FaucetError(RuntimeError):
+    pass
+
+
+class JunctionRec(C.Structure):
+    _fields_ = [("kmer", C.c_uint64), ("dist", C.c_uint8 * 5), ("cov", C.c_uint8 * 4), ("linked", C.c_uint8 * 5),
+                ("pad", C.c_uint8 * 2), ("creation_rank", C.c_uint64)]
+
+
+REC_DTYPE = np.dtype([("kmer", "<u8"), ("dist", "u1", 5), ("cov", "u1", 4), ("linked", "u1", 5), ("pad", "u1", 2),
+                      ("creation_rank", "<u8")])
+assert REC_DTYPE.itemsize == C.sizeof(JunctionRec) == 32
+
+
+class ScanStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_junctions", "nb_jcheck_kmer", "nb_no_juncs", "nb_processed",
+                                           "nb_skipped", "reads_no_errors", "reads_processed",
+                                           "unambiguous_reads")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class LoadStats(C.Structure):
+    _fields_ = [("reads_processed", C.c_uint64), ("unambiguous_reads", C.c_uint64), ("kmers", C.c_uint64),
+                ("weight1", C.c_double), ("weight2", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+_recpp = C.POINTER(C.POINTER(JunctionRec))
+
+
+def _load():
+    if not os.path.exists(_SO):
+        raise FaucetError(f"{_SO} is missing: build it with `make -C faucet_b200/csrc` "
+                          "(or __graft_entry__.build()); there is no fallback path")
+    L = C.CDLL(_SO)
+    L.faucet_gpu_last_error.restype = C.c_char_p
+    L.faucet_gpu_version.restype = C.c_char_p
+    L.faucet_gpu_init.argtypes = [C.c_int]
+    L.faucet_geometry_from_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_float, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for f in (L.faucet_geometry_optimal, L.faucet_geometry_2_hash):
+        f.argtypes = [C.c_uint64, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.faucet_gpu_load_two_filters.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p,
+                                              C.POINTER(LoadStats)]
+    L.faucet_gpu_load_two_filters_mem.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                                  _u8p, C.POINTER(LoadStats)]
+    scan_tail = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int,
+                 _u8p, C.c_int, C.c_int, _recpp, _u64p, C.POINTER(ScanStats)]
+    L.faucet_gpu_scan.argtypes = [C.c_char_p] + scan_tail
+    L.faucet_gpu_scan_mem.argtypes = [C.c_void_p, C.c_size_t] + scan_tail
+    L.faucet_gpu_free.argtypes = [C.c_void_p]
+    L.faucet_gpu_set_batch_bytes.argtypes = [C.c_size_t]
+    L.faucet_gpu_set_epoch_limit.argtypes = [C.c_uint64]
+    vp = C.c_void_p
+    L.faucet_session_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t]
+    L.faucet_session_destroy.argtypes = [vp]
+    L.faucet_session_set_text.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int]
+    L.faucet_session_reset_filters.argtypes = [vp]
+    L.faucet_session_parse.argtypes = [vp, C.c_int]
+    L.faucet_session_load.argtypes = [vp]
+    L.faucet_session_scan_flags.argtypes = [vp]
+    L.faucet_session_stitch.argtypes = [vp, C.c_int, C.c_int, _u64p]
+    L.faucet_session_get_bloom.argtypes = [vp, _u8p, _u8p]
+    L.faucet_session_set_bloom.argtypes = [vp, _u8p]
+    L.faucet_session_get_junctions.argtypes = [vp, _recpp, _u64p, C.POINTER(ScanStats)]
+    L.faucet_session_sync.argtypes = [vp]
+    L.faucet_session_stream.argtypes = [vp]
+    L.faucet_session_stream.restype = C.c_void_p
+    L.faucet_session_timer_start.argtypes = [vp]
+    L.faucet_session_timer_stop_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.faucet_session_kernel_launches.argtypes = [vp]
+    L.faucet_session_kernel_launches.restype = C.c_uint64
+    L.faucet_session_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _u64p]
+    L.faucet_session_set_profiling.argtypes = [vp, C.c_int]
+    L.faucet_session_load_stats.argtypes = [vp, C.POINTER(LoadStats), C.c_uint64]
+    return L
+
+
+lib = _load()
+
+
+def _check(rc):
+    if rc != 0:
+        raise FaucetError(f"libfaucet_gpu error {rc}: {lib.faucet_gpu_last_error().decode()}")
+
+
+def _ptr(a, t=_u8p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def device_count():
+    return lib.faucet_gpu_device_count()
+
+
+def set_batch_bytes(n):
+    _check(lib.faucet_gpu_set_batch_bytes(n))
+
+
+def set_epoch_limit(n):
+    _check(lib.faucet_gpu_set_epoch_limit(n))
+
+
+def geometry_from_reads(estimated_kmers, singletons, fp=0.04):
+    """(p1, log2_tai, n_hash) as getBloomFilterFromReads derives them (src/Faucet.cpp:204-219)"""
+    p1, a, b = C.c_double(), C.c_int(), C.c_int()
+    _check(lib.faucet_geometry_from_reads(estimated_kmers, singletons, fp, C.byref(p1), C.byref(a), C.byref(b)))
+    return p1.value, a.value, b.value
+
+
+def geometry_optimal(items, fp):
+    a, b = C.c_int(), C.c_int()
+    _check(lib.faucet_geometry_optimal(items, fp, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def geometry_2_hash(items, fp):
+    a, b = C.c_int(), C.c_int()
+    _check(lib.faucet_geometry_2_hash(items, fp, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _as_buffer(text):
+    """bytes / numpy uint8 array / (address, nbytes) -> (address, nbytes, keepalive)"""
+    if isinstance(text, tuple):
+        return text[0], text[1], None
+    if isinstance(text, (bytes, bytearray)):
+        arr = np.frombuffer(text, np.uint8)
+        return arr.ctypes.data, arr.size, arr
+    arr = np.ascontiguousarray(text).view(np.uint8)
+    return arr.ctypes.data, arr.size, arr
+
+
+def load_two_filters_mem(text, fastq, k, log2_tai, n_hash, want_bloo1=False, out=None):
+    """pass 1 over FASTA/FASTQ text in host memory -> (bloo2, bloo1 | None, LoadStats)"""
+    addr, n, keep = _as_buffer(text)
+    nb = (1 << log2_tai) // 8
+    b2 = np.empty(nb, np.uint8) if out is None else out
+    b1 = np.empty(nb, np.uint8) if want_bloo1 else None
+    st = LoadStats()
+    _check(lib.faucet_gpu_load_two_filters_mem(addr, n, int(fastq), k, log2_tai, n_hash, _ptr(b2), _ptr(b1),
+                                               C.byref(st)))
+    return b2, b1, st
+
+
+def load_two_filters(path, fastq, k, log2_tai, n_hash, want_bloo1=False):
+    nb = (1 << log2_tai) // 8
+    b2 = np.empty(nb, np.uint8)
+    b1 = np.empty(nb, np.uint8) if want_bloo1 else None
+    st = LoadStats()
+    _check(lib.faucet_gpu_load_two_filters(path.encode(), int(fastq), k, log2_tai, n_hash, _ptr(b2), _ptr(b1),
+                                           C.byref(st)))
+    return b2, b1, st
+
+
+def _take_recs(recs, n):
+    arr = np.zeros(n.value, REC_DTYPE)
+    if n.value:
+        C.memmove(arr.ctypes.data, recs, n.value * REC_DTYPE.itemsize)
+    lib.faucet_gpu_free(recs)
+    return arr
+
+
+def scan_mem(text, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, log2_tai, n_hash, spf=None,
+             spf_geom=(0, 0), lpf=None, lpf_geom=(0, 0)):
+    """pass 2 over text in host memory -> (records sorted by creation rank, stats dict)"""
+    addr, n, keep = _as_buffer(text)
+    recs, cnt, st = C.POINTER(JunctionRec)(), C.c_uint64(), ScanStats()
+    _check(lib.faucet_gpu_scan_mem(addr, n, int(fastq), int(paired_ends), int(no_cleaning), k, j, max_spacer_dist,
+                                   _ptr(bloo2), log2_tai, n_hash, _ptr(spf), spf_geom[0], spf_geom[1], _ptr(lpf),
+                                   lpf_geom[0], lpf_geom[1], C.byref(recs), C.byref(cnt), C.byref(st)))
+    return _take_recs(recs, cnt), st.as_dict()
+
+
+def scan(path, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, log2_tai, n_hash, spf=None,
+         spf_geom=(0, 0), lpf=None, lpf_geom=(0, 0)):
+    recs, cnt, st = C.POINTER(JunctionRec)(), C.c_uint64(), ScanStats()
+    _check(lib.faucet_gpu_scan(path.encode(), int(fastq), int(paired_ends), int(no_cleaning), k, j, max_spacer_dist,
+                               _ptr(bloo2), log2_tai, n_hash, _ptr(spf), spf_geom[0], spf_geom[1], _ptr(lpf),
+                               lpf_geom[0], lpf_geom[1], C.byref(recs), C.byref(cnt), C.byref(st)))
+    return _take_recs(recs, cnt), st.as_dict()
+
+
+class Session:
+    """device-resident stage API (faucet_session_* in include/faucet_gpu.h)"""
+    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4}
+
+    def __init__(self, k, log2_tai, n_hash, j=1, max_spacer_dist=100, max_text_bytes=1 << 30):
+        self.h = C.c_void_p()
+        _check(lib.faucet_session_create(C.byref(self.h), k, log2_tai, n_hash, j, max_spacer_dist, max_text_bytes))
+        self.k, self.log2_tai, self.n_hash = k, log2_tai, n_hash
+
+    def close(self):
+        if self.h:
+            lib.faucet_session_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_text(self, text, device=False):
+        addr, n, keep = _as_buffer(text)
+        _check(lib.faucet_session_set_text(self.h, addr, n, int(device)))
+
+    def reset_filters(self):
+        _check(lib.faucet_session_reset_filters(self.h))
+
+    def parse(self, fastq):
+        _check(lib.faucet_session_parse(self.h, int(fastq)))
+
+    def load(self):
+        _check(lib.faucet_session_load(self.h))
+
+    def scan_flags(self):
+        _check(lib.faucet_session_scan_flags(self.h))
+
+    def stitch(self, paired_ends, no_cleaning):
+        n = C.c_uint64()
+        _check(lib.faucet_session_stitch(self.h, int(paired_ends), int(no_cleaning), C.byref(n)))
+        return n.value
+
+    def get_bloom(self, want_bloo1=False, to_host=True):
+        nb = (1 << self.log2_tai) // 8
+        b2 = np.empty(nb, np.uint8) if to_host else None
+        b1 = np.empty(nb, np.uint8) if (want_bloo1 and to_host) else None
+        _check(lib.faucet_session_get_bloom(self.h, _ptr(b2), _ptr(b1)))
+        return b2, b1
+
+    def set_bloom(self, bloo2):
+        _check(lib.faucet_session_set_bloom(self.h, _ptr(bloo2)))
+
+    def load_stats(self, total_lines=0):
+        st = LoadStats()
+        _check(lib.faucet_session_load_stats(self.h, C.byref(st), total_lines))
+        return st
+
+    def junctions(self):
+        recs, cnt, st = C.POINTER(JunctionRec)(), C.c_uint64(), ScanStats()
+        _check(lib.faucet_session_get_junctions(self.h, C.byref(recs), C.byref(cnt), C.byref(st)))
+        return _take_recs(recs, cnt), st.as_dict()
+
+    def sync(self):
+        _check(lib.faucet_session_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib.faucet_session_stream(self.h)
+
+    def timer_start(self):
+        _check(lib.faucet_session_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        _check(lib.faucet_session_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on):
+        _check(lib.faucet_session_set_profiling(self.h, int(on)))
+
+    def kernel_ms(self, name):
+        ms, n = C.c_float(), C.c_uint64()
+        _check(lib.faucet_session_kernel_ms(self.h, self.KERNELS[name], C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launches(self):
+        return lib.faucet_session_kernel_launches(self.h)

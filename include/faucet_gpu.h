@@ -1,0 +1,146 @@
+/* faucet_gpu.h -- C ABI of libfaucet_gpu.so: the B200 (sm_100a) implementation of Faucet's two-pass
+ * streaming k-mer hot path (pass 1 "Bloom load", pass 2 "junction scan").
+ *
+ * The reference (Shamir-Lab/Faucet) has no FFI; the boundary is the handful of C++ calls that
+ * src/Faucet.cpp's main() makes.  Each entry point below names the reference call it replaces.
+ * Plain pointers and sizes only; all host pointers are caller-owned; every function returns 0 on
+ * success or a negative FAUCET_E_* code, with faucet_gpu_last_error() giving the message.
+ * The library is callable from one host thread at a time and owns its CUDA streams internally.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * FAUCET_E_NO_DEVICE.
+ */
+#ifndef FAUCET_GPU_H
+#define FAUCET_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAUCET_E_NO_DEVICE -1
+#define FAUCET_E_CUDA -2
+#define FAUCET_E_ARG -3
+#define FAUCET_E_IO -4
+#define FAUCET_E_NOMEM -5
+#define FAUCET_E_STATE -6
+
+/* utils/Junction.h:10-53 (14-byte POD) + its key + the creation rank the host needs to re-insert
+ * records into std::unordered_map in the reference's insertion order. */
+typedef struct {
+  uint64_t kmer;          /* oriented k-mer, ReadKmer::getKmer (utils/ReadKmer.cpp:50-57) */
+  uint8_t dist[5];        /* utils/Junction.h:18 */
+  uint8_t cov[4];         /* utils/Junction.h:12 */
+  uint8_t linked[5];      /* utils/Junction.h:19 */
+  uint8_t pad[2];
+  uint64_t creation_rank; /* 0,1,2,... in the order the reference would have created them */
+} faucet_junction_rec;    /* 32 bytes */
+
+/* counters printed by ReadScanner::printScanSummary / scanReads (src/ReadScanner.cpp:19-27,352-358) */
+typedef struct {
+  uint64_t n_junctions, nb_jcheck_kmer, nb_no_juncs, nb_processed, nb_skipped, reads_no_errors,
+      reads_processed, unambiguous_reads;
+} faucet_scan_stats;
+
+/* what load_two_filters prints (utils/Bloom.cpp:345-349) */
+typedef struct {
+  uint64_t reads_processed, unambiguous_reads, kmers;
+  double weight1, weight2; /* Bloom::weight() of bloo1 / bloo2 after the load */
+} faucet_load_stats;
+
+/* device-side timings of the last call, milliseconds (CUDA events on the library's stream) */
+typedef struct {
+  float h2d_ms, parse_ms, load_ms, scan_ms, stitch_ms, d2h_ms, total_ms;
+  uint64_t kernel_launches;
+} faucet_timings;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int faucet_gpu_init(int device);          /* cudaSetDevice + stream creation; idempotent */
+void faucet_gpu_shutdown(void);
+const char* faucet_gpu_last_error(void);
+int faucet_gpu_device_count(void);        /* 0 when no CUDA device / driver */
+const char* faucet_gpu_version(void);
+
+/* ---- Bloom geometry, host side, bit-for-bit what the reference derives ------------------- */
+/* getBloomFilterFromReads: p1 = brents_fun(my_func, fp, .5, 1e-4, 1000) then
+ * create_bloom_filter_optimal(estimated_kmers, (float)p1)   (src/Faucet.cpp:197-223) */
+int faucet_geometry_from_reads(uint64_t estimated_kmers, uint64_t singletons, float fp, double* p1_out,
+                               int* log2_tai_out, int* n_hash_out);
+/* Bloom::create_bloom_filter_optimal (utils/Bloom.cpp:229-247) */
+int faucet_geometry_optimal(uint64_t estimated_items, float fp, int* log2_tai_out, int* n_hash_out);
+/* Bloom::create_bloom_filter_2_hash (utils/Bloom.cpp:206-226), used only with -bloom_file */
+int faucet_geometry_2_hash(uint64_t estimated_items, float fp, int* log2_tai_out, int* n_hash_out);
+
+/* ---- pass 1: replaces load_two_filters(bloo1, bloo2, file, fastq, mercy=false) ------------
+ * (utils/Bloom.h:294, utils/Bloom.cpp:267-350).  bloo2_out: tai/8 bytes, reference bit layout
+ * (bit h <-> byte h>>3, mask 1<<(h&7)); bloo1_out may be NULL.  The arrays are OVERWRITTEN (the
+ * reference's filters start zeroed, utils/Bloom.cpp:184-186). */
+int faucet_gpu_load_two_filters(const char* reads_path, int fastq, int k, int log2_tai, int n_hash,
+                                uint8_t* bloo2_out, uint8_t* bloo1_out, faucet_load_stats* stats);
+/* same, over FASTA/FASTQ text already in host memory (pinned or pageable) */
+int faucet_gpu_load_two_filters_mem(const char* text, size_t n, int fastq, int k, int log2_tai,
+                                    int n_hash, uint8_t* bloo2_out, uint8_t* bloo1_out,
+                                    faucet_load_stats* stats);
+
+/* ---- pass 2: replaces ReadScanner::scanReads(fastq, paired_ends, no_cleaning) -------------
+ * (src/ReadScanner.h:66-67, src/ReadScanner.cpp:284-359) together with the JunctionMap it fills
+ * (utils/JunctionMap.h:61).  short_pf / long_pf are in/out pair filters
+ * (src/Faucet.cpp:265-281), either may be NULL.  *recs_out is allocated by the library, sorted by
+ * creation_rank; release it with faucet_gpu_free. */
+int faucet_gpu_scan(const char* reads_path, int fastq, int paired_ends, int no_cleaning, int k, int j,
+                    int max_spacer_dist, const uint8_t* bloo2, int log2_tai, int n_hash,
+                    uint8_t* short_pf, int spf_log2_tai, int spf_n_hash, uint8_t* long_pf,
+                    int lpf_log2_tai, int lpf_n_hash, faucet_junction_rec** recs_out,
+                    uint64_t* n_recs_out, faucet_scan_stats* stats);
+int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, int no_cleaning, int k,
+                        int j, int max_spacer_dist, const uint8_t* bloo2, int log2_tai, int n_hash,
+                        uint8_t* short_pf, int spf_log2_tai, int spf_n_hash, uint8_t* long_pf,
+                        int lpf_log2_tai, int lpf_n_hash, faucet_junction_rec** recs_out,
+                        uint64_t* n_recs_out, faucet_scan_stats* stats);
+void faucet_gpu_free(void* p);
+
+/* ---- tuning / introspection -------------------------------------------------------------- */
+/* bytes of read text per device batch (default 1 GiB; tests use tiny values to exercise the
+ * multi-batch path) and the timestamp epoch length (default 2^32-2) */
+int faucet_gpu_set_batch_bytes(size_t bytes);
+int faucet_gpu_set_epoch_limit(uint64_t stamps);
+int faucet_gpu_get_timings(faucet_timings* out);
+
+/* ---- device-resident stage API (bench.py "value": inputs already in HBM) ------------------
+ * A session owns the device buffers for one (k, geometry, j, spacer) configuration. */
+typedef struct faucet_session faucet_session;
+int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash, int j,
+                          int max_spacer_dist, size_t max_text_bytes);
+void faucet_session_destroy(faucet_session* s);
+/* copy text into the session's device batch buffer (host or device source pointer) */
+int faucet_session_set_text(faucet_session* s, const void* text, size_t n, int src_is_device);
+int faucet_session_reset_filters(faucet_session* s);           /* zero bloo1/bloo2/stamps */
+int faucet_session_parse(faucet_session* s, int fastq);        /* text -> 2-bit + validity planes */
+int faucet_session_load(faucet_session* s);                    /* pass 1 over the parsed batch */
+int faucet_session_scan_flags(faucet_session* s);              /* pass 2, order-free part */
+int faucet_session_stitch(faucet_session* s, int paired_ends, int no_cleaning,
+                          uint64_t* n_junctions_out);          /* pass 2, stream-order part */
+/* multi-batch form of the stitch: begin once (pair filters may be NULL), then one call per batch */
+int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_cleaning, uint8_t* short_pf,
+                                int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai,
+                                int lpf_n_hash);
+int faucet_session_stitch_batch(faucet_session* s, const uint8_t* host_text, size_t valid_bytes);
+int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_t total_lines);
+int faucet_session_set_profiling(faucet_session* s, int on);   /* per-kernel CUDA-event timing */
+int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* bloo1_out);
+int faucet_session_set_bloom(faucet_session* s, const uint8_t* bloo2);
+int faucet_session_get_junctions(faucet_session* s, faucet_junction_rec** recs_out, uint64_t* n_out,
+                                 faucet_scan_stats* stats);
+int faucet_session_sync(faucet_session* s);
+void* faucet_session_stream(faucet_session* s);                /* cudaStream_t the kernels run on */
+/* CUDA-event timing of the stages on the session stream */
+int faucet_session_timer_start(faucet_session* s);
+int faucet_session_timer_stop_ms(faucet_session* s, float* ms_out);
+uint64_t faucet_session_kernel_launches(faucet_session* s);
+/* event-timed duration (ms) accumulated per named kernel since the last reset:
+ * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch */
+int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

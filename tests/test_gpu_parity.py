@@ -1,0 +1,175 @@
+"""GPU parity: libfaucet_gpu.so (through its C ABI) against the oracle on the same seeded inputs.
+
+Bit-exact bar: identical bloo1/bloo2 byte arrays, identical junction records (key, dist, cov, linked)
+in identical creation order, identical pair filters and identical scan counters.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from _oracle import gen_reads, sort_recs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import faucet_b200
+    if faucet_b200.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests need the B200 box")
+    return faucet_b200
+
+
+def _dataset(tmp_path_factory, name, **kw):
+    p = str(tmp_path_factory.mktemp("reads") / name)
+    gen_reads(p, **kw)
+    with open(p, "rb") as f:
+        return p, f.read()
+
+
+@pytest.fixture(scope="module")
+def small_fq(tmp_path_factory):
+    # 100 kbp genome, 30x, 0.5% errors, N bases (multi-segment reads), planted repeats
+    return _dataset(tmp_path_factory, "small.fq", genome=100000, cov=30, length=100, insert=300, seed=3,
+                    err=0.005, nrate=0.002, repeats=True)
+
+
+@pytest.fixture(scope="module")
+def small_fa(tmp_path_factory):
+    return _dataset(tmp_path_factory, "small.fa", genome=60000, cov=20, length=150, insert=400, seed=5,
+                    err=0.01, nrate=0.004, fasta=True)
+
+
+def _geom(oracle, est, sing, fp=0.04):
+    p1 = ctypes.c_float(oracle.lib.fo_brent_p1(est, sing, fp)).value
+    return oracle.geometry_optimal(est, p1)
+
+
+def _strip(recs):
+    """drop creation_rank/pad so GPU (32-byte) and oracle (24-byte) records compare field by field"""
+    return [(int(r["kmer"]), bytes(r["dist"]), bytes(r["cov"]), bytes(r["linked"])) for r in recs]
+
+
+@pytest.mark.parametrize("k", [31, 21, 32])
+def test_load_matches_oracle(fb, oracle, small_fq, k):
+    _, text = small_fq
+    lt, nh = _geom(oracle, 100000, 50000)
+    o1, o2, ost = oracle.load_two_filters(text, True, k, lt, nh)
+    g2, g1, gst = fb.load_two_filters_mem(text, True, k, lt, nh, want_bloo1=True)
+    assert np.array_equal(g1, o1)
+    assert np.array_equal(g2, o2)
+    assert gst.kmers == ost.kmers
+    assert gst.unambiguous_reads == ost.unambiguous_reads
+    assert gst.reads_processed == ost.reads_processed
+    assert gst.weight1 == ost.weight1 and gst.weight2 == ost.weight2
+
+
+@pytest.mark.parametrize("nh,lt", [(1, 18), (2, 19), (3, 20), (4, 17), (6, 21), (7, 22), (10, 22)])
+def test_load_hash_counts(fb, oracle, small_fa, nh, lt):
+    _, text = small_fa
+    o1, o2, _ = oracle.load_two_filters(text, False, 27, lt, nh)
+    g2, g1, _ = fb.load_two_filters_mem(text, False, 27, lt, nh, want_bloo1=True)
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+
+
+def test_load_multibatch_and_epochs(fb, oracle, small_fq):
+    """tiny batches (cuts at record boundaries) and a tiny stamp epoch give the same filters"""
+    _, text = small_fq
+    lt, nh = _geom(oracle, 100000, 50000)
+    o1, o2, ost = oracle.load_two_filters(text, True, 31, lt, nh)
+    try:
+        fb.set_batch_bytes(200_000)
+        fb.set_epoch_limit(500_000)
+        g2, g1, gst = fb.load_two_filters_mem(text, True, 31, lt, nh, want_bloo1=True)
+    finally:
+        fb.set_batch_bytes(1 << 30)
+        fb.set_epoch_limit(0xfffffffe)
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    assert gst.kmers == ost.kmers and gst.reads_processed == ost.reads_processed
+
+
+@pytest.mark.parametrize("j", [0, 1, 2])
+@pytest.mark.parametrize("no_cleaning", [1, 0])
+def test_scan_matches_oracle(fb, oracle, small_fq, j, no_cleaning):
+    _, text = small_fq
+    k = 31
+    lt, nh = _geom(oracle, 100000, 50000)
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    sg, lg = oracle.geometry_optimal(100000 // 20, 0.01), oracle.geometry_optimal(100000 // 10, 0.01)
+    ospf, olpf = np.zeros((1 << sg[0]) // 8, np.uint8), np.zeros((1 << lg[0]) // 8, np.uint8)
+    gspf, glpf = ospf.copy(), olpf.copy()
+    orecs, ost = oracle.scan(text, True, True, no_cleaning, k, j, 100, b2, lt, nh, ospf, sg, olpf, lg)
+    grecs, gst = fb.scan_mem(text, True, True, no_cleaning, k, j, 100, b2, lt, nh, gspf, sg, glpf, lg)
+    assert gst == ost
+    assert _strip(grecs) == _strip(orecs)          # same records in the same creation order
+    assert list(grecs["creation_rank"]) == list(range(len(grecs)))
+    assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
+
+
+def test_scan_fasta_spacers_multibatch(fb, oracle, small_fa):
+    """150 bp reads with max_spacer_dist 40 (spacers fire), FASTA, unpaired, tiny batches"""
+    _, text = small_fa
+    k = 25
+    lt, nh = 21, 3
+    _, b2, _ = oracle.load_two_filters(text, False, k, lt, nh)
+    orecs, ost = oracle.scan(text, False, False, 1, k, 1, 40, b2, lt, nh)
+    try:
+        fb.set_batch_bytes(150_000)
+        grecs, gst = fb.scan_mem(text, False, False, 1, k, 1, 40, b2, lt, nh)
+    finally:
+        fb.set_batch_bytes(1 << 30)
+    assert gst == ost
+    assert _strip(grecs) == _strip(orecs)
+
+
+@pytest.mark.parametrize("tail", [b"", b"\n", b"@last", b"@lastACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT",
+                                  b"@h\nACGTNACG", b"@h\nACGTACGTACGTAGCTAGCTAGCTAGCATCGATCGATCAGCTAGC\n+", b"\n\n"])
+def test_ragged_tails(fb, oracle, small_fq, tail):
+    """truncated / unterminated inputs, including the header-reused-as-sequence getline quirk"""
+    _, text = small_fq
+    text = text[:40_000]
+    text = text[:text.rfind(b"\n@") + 1] + tail
+    k, lt, nh = 15, 18, 3
+    o1, o2, ost = oracle.load_two_filters(text, True, k, lt, nh)
+    g2, g1, gst = fb.load_two_filters_mem(text, True, k, lt, nh, want_bloo1=True)
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    assert gst.reads_processed == ost.reads_processed and gst.kmers == ost.kmers
+    orecs, osst = oracle.scan(text, True, True, 1, k, 1, 100, o2, lt, nh)
+    grecs, gsst = fb.scan_mem(text, True, True, 1, k, 1, 100, o2, lt, nh)
+    assert gsst == osst and _strip(grecs) == _strip(orecs)
+
+
+def test_empty_and_tiny_inputs(fb, oracle):
+    k, lt, nh = 31, 16, 4
+    for text in (b"", b"\n", b">x\n", b">x\nACGT\n", b">x\n" + b"ACGT" * 8 + b"\n",
+                 b">x\n" + b"ACGT" * 7 + b"ACG" + b"\n", b">x\r\n" + b"ACGT" * 10 + b"\r\n"):
+        o1, o2, ost = oracle.load_two_filters(text, False, k, lt, nh)
+        g2, g1, gst = fb.load_two_filters_mem(text, False, k, lt, nh, want_bloo1=True)
+        assert np.array_equal(g1, o1) and np.array_equal(g2, o2), text
+        assert gst.kmers == ost.kmers and gst.reads_processed == ost.reads_processed, text
+        orecs, osst = oracle.scan(text, False, False, 1, k, 1, 100, o2, lt, nh)
+        grecs, gsst = fb.scan_mem(text, False, False, 1, k, 1, 100, o2, lt, nh)
+        assert gsst == osst and _strip(grecs) == _strip(orecs), text
+
+
+def test_session_stage_api(fb, oracle, small_fq):
+    """the device-resident stage API gives the same answer as the whole-pass calls"""
+    _, text = small_fq
+    k = 31
+    lt, nh = _geom(oracle, 100000, 50000)
+    _, o2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    orecs, ost = oracle.scan(text, True, True, 1, k, 1, 100, o2, lt, nh)
+    s = fb.Session(k, lt, nh, j=1, max_spacer_dist=100, max_text_bytes=len(text))
+    s.set_text(text)
+    s.parse(True)
+    s.load()
+    b2, _ = s.get_bloom()
+    assert np.array_equal(b2, o2)
+    s.scan_flags()
+    assert s.stitch(True, True) == len(orecs)
+    grecs, gst = s.junctions()
+    assert _strip(grecs) == _strip(orecs)
+    assert s.launches > 0
+    s.close()
