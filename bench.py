@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers/s of the Faucet hot path (Bloom load + junction scan) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+
+A "step" = one pass of the hot path (parse + pass 1 load + pass 2 scan incl. stitch) over one batch of
+synthetic reads of BASELINE.json's configs[1] shape (4.6 Mbp genome, 100x, 150 bp paired-end FASTQ,
+k=31, --two_hash which is a no-op on the from-reads path).  Prints ONE JSON line (see DESIGN.md
+"Measurement" for every field).  oracle/ is used here only for the cpu_baseline / reference arm.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: genome, coverage, read length, insert, k, estimated_kmers, singletons, flags
+    "c1": dict(genome=1_000_000, cov=30, length=100, insert=300, k=31, est=1_000_000, sing=10_000,
+               desc="synthetic 1 Mbp random genome, 30x interlaced 100bp paired-end fastq, k=31"),
+    "c2": dict(genome=4_600_000, cov=100, length=150, insert=500, k=31, est=4_600_000, sing=1_000_000,
+               desc="synthetic E. coli-sized 4.6 Mbp genome, 100x 150bp paired-end, k=31, --two_hash"),
+    "c3": dict(genome=64_000_000, cov=50, length=100, insert=300, k=27, est=64_000_000, sing=20_000_000,
+               desc="synthetic 64 Mbp (chr20-sized) genome, 50x 100bp paired-end, k=27"),
+}
+J, MAX_SPACER, FP = 1, 100, 0.04  # faucet defaults: -j 1, -max_spacer_dist 100, -fp 0.04 (src/Faucet.h:14-48)
+
+
+def gen_dataset(w, seed, pairs=None, tag=""):
+    from _oracle import gen_reads
+    d = os.environ.get("FAUCET_BENCH_TMP", "/tmp/faucet_bench")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"{w['genome']}_{w['cov']}_{w['length']}_{seed}{tag}.fq")
+    if not os.path.exists(path):
+        kw = dict(genome=w["genome"], cov=w["cov"], length=w["length"], insert=w["insert"], seed=seed)
+        if pairs:
+            kw["pairs"] = pairs
+        gen_reads(path + ".tmp", **kw)
+        os.replace(path + ".tmp", path)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.p = gpu, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def algorithmic_bytes(w, n_hash, weight2, r_contained):
+    """SURVEY.md section 8(d) sector model, bytes per k-mer"""
+    rho = w["length"] / (w["length"] - w["k"] + 1)
+    m = (1 - weight2 ** n_hash) / (1 - weight2)
+    a_load = rho + 32 * n_hash * (1 + r_contained)
+    a_scan = rho + 32 * (n_hash + 6 * m)
+    return a_load, a_scan
+
+
+def cpu_reference_sample(w, k, lt, nh, path, n_reads, repeats=1):
+    """times the reference's own CPU implementation (oracle/_ref, unmodified sources) or, if it was
+    not built, the C port in oracle/ on the first n_reads reads of the workload; 1 thread (the
+    reference is single-threaded)."""
+    import numpy as np
+    from _oracle import Oracle, Ref, have_ref
+    lines = n_reads * 4
+    sample = path + f".head{n_reads}"
+    if not os.path.exists(sample):
+        with open(path, "rb") as f, open(sample, "wb") as g:
+            for _ in range(lines):
+                ln = f.readline()
+                if not ln:
+                    break
+                g.write(ln)
+    text = open(sample, "rb").read()
+    kmers = (text.count(b"\n") // 4) * (w["length"] - k + 1)
+    times = []
+    kind = "reference" if have_ref() else "port"
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            r = Ref()
+            _, b2 = r.load_two_filters(sample, True, k, lt, nh)
+            r.scan(sample, True, True, 1, k, J, MAX_SPACER, b2, lt, nh)
+        else:
+            o = Oracle()
+            _, b2, _ = o.load_two_filters(text, True, k, lt, nh)
+            o.scan(text, True, True, 1, k, J, MAX_SPACER, b2, lt, nh)
+        times.append(time.perf_counter() - t0)
+    return kind, kmers, times, f"first {n_reads} reads of the workload file, load+scan, --no_cleaning, full-size Bloom geometry"
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import faucet_b200 as fb  # geometry only (host code); no GPU work in this arm
+    k = w["k"]
+    _, lt, nh = fb.geometry_from_reads(w["est"], w["sing"], FP)
+    path = gen_dataset(w, seed=1)
+    n_reads = int(os.environ.get("FAUCET_REF_SAMPLE_READS", "60000"))
+    kind, kmers, times, sample = cpu_reference_sample(w, k, lt, nh, path, n_reads, repeats=args.steps + args.warmup)
+    timed = times[args.warmup:]
+    val = kmers * len(timed) / sum(timed)
+    print(json.dumps({
+        "impl": "reference", "metric": "k-mers/sec (Bloom load + junction scan)", "value": val, "unit": "k-mers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(timed) / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": w["desc"], "k": k, "log2_tai": lt, "n_hash": nh, "j": J},
+        "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args, w):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import faucet_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or fb.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: libfaucet_gpu has no CPU path")
+    torch.cuda.set_device(local)
+    fb._lib._check(fb.lib.faucet_gpu_init(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    k = w["k"]
+    _, lt, nh = fb.geometry_from_reads(w["est"], w["sing"], FP)
+    # weak scaling: every rank streams its own read set of the named shape (different seed per rank)
+    path = gen_dataset(w, seed=1 + rank)
+    raw = np.fromfile(path, dtype=np.uint8)
+    n_text = raw.size
+    reads = int(np.count_nonzero(raw == 10)) // 4
+    kmers_per_pass = reads * (w["length"] - k + 1)
+    host = torch.empty(n_text, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = raw
+    del raw
+    dev = host.cuda()
+
+    sess = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=n_text)
+
+    def step_resident():
+        sess.set_text((dev.data_ptr(), n_text), device=True)  # D2D: the batch is already in HBM
+        sess.reset_filters()
+        sess.parse(True)
+        sess.load()
+        sess.get_bloom(to_host=False)
+        sess.scan_flags()
+        return sess.stitch(True, True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        n_junc = step_resident()
+    sess.sync()
+    sess.set_profiling(True)
+    launches0 = sess.launches
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    sess.timer_start()
+    for _ in range(args.steps):
+        n_junc = step_resident()
+    ms = sess.timer_stop_ms()
+    barrier()
+    clk = clocks.stop()
+    launches = sess.launches - launches0
+    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags")}
+    sess.set_profiling(False)
+    lstats = sess.load_stats()
+    b2, _ = sess.get_bloom()
+    weight2 = float(np.unpackbits(b2).sum()) / (1 << lt)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + D2H inside the timed region
+    hptr = (host.data_ptr(), n_text)
+    bloo2 = np.empty((1 << lt) // 8, np.uint8)
+
+    def step_e2e():
+        fb.load_two_filters_mem(hptr, True, k, lt, nh, out=bloo2)
+        recs, st = fb.scan_mem(hptr, True, True, True, k, J, MAX_SPACER, bloo2, lt, nh)
+        return len(recs)
+
+    sess.close()
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        n_junc_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert n_junc_e2e == n_junc
+
+    # max over ranks, whole-job aggregate
+    t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(kmers_per_pass)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_all, e2e_ms_all = t.tolist()
+    kmers_all = tot.item()
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        r_contained = 1.0 - (lstats.fresh_kmers / lstats.kmers if lstats.kmers else 0.0)
+        a_load, a_scan = algorithmic_bytes(w, nh, weight2, r_contained)
+        dom = max(("load_A", "scan_flags"), key=lambda n: kernel_ms[n][0])
+        per_launch_ms = kernel_ms[dom][0] / max(1, kernel_ms[dom][1])
+        a_dom = a_scan if dom == "scan_flags" else a_load
+        achieved = kmers_per_pass * a_dom / (per_launch_ms * 1e-3) / 1e9
+        out = {
+            "metric": "k-mers/sec (Bloom load + junction scan)", "value": kmers_all * args.steps / (ms_all * 1e-3),
+            "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": w["desc"], "k": k, "log2_tai": lt, "n_hash": nh, "j": J,
+                       "max_spacer_dist": MAX_SPACER, "reads_per_gpu": reads, "kmers_per_pass_per_gpu": kmers_per_pass,
+                       "text_bytes_per_gpu": n_text, "junctions": int(n_junc),
+                       "l2": "inputs (%.0f MB text + planes) exceed the 126 MB L2" % (n_text / 1e6),
+                       "parallelism": "replicated read sets, one per GPU" if world > 1 else "single GPU"},
+            "e2e": {"value": kmers_all / (e2e_ms_all * 1e-3), "unit": "k-mers/s",
+                    "h2d_bytes_per_step": 2 * n_text + bloo2.nbytes,
+                    "d2h_bytes_per_step": bloo2.nbytes + n_text + 32 * int(n_junc), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms},
+            "kernels_ms_per_step": {n: v[0] / args.steps for n, v in kernel_ms.items()},
+            "bloom_weight2": weight2, "contained_fraction": r_contained,
+        }
+        if args.cpu_baseline:
+            kind, ck, times, sample = cpu_reference_sample(w, k, lt, nh, path, int(os.environ.get("FAUCET_REF_SAMPLE_READS", "60000")))
+            out["cpu_baseline"] = {"value": ck / times[0], "unit": "k-mers/s", "cores": 1, "kind": kind, "sample": sample}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not os.environ.get("FAUCET_BENCH_PROFILE_RUN"):
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

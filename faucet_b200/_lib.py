@@ -33,7 +33,7 @@ class ScanStats(C.Structure):
 
 class LoadStats(C.Structure):
     _fields_ = [("reads_processed", C.c_uint64), ("unambiguous_reads", C.c_uint64), ("kmers", C.c_uint64),
-                ("weight1", C.c_double), ("weight2", C.c_double)]
+                ("fresh_kmers", C.c_uint64), ("weight1", C.c_double), ("weight2", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

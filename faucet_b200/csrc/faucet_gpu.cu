@@ -408,6 +408,7 @@ int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_
   CU(cudaStreamSynchronize(s->stream));
   out->kmers = c.kmers;
   out->unambiguous_reads = c.segments;
+  out->fresh_kmers = c.fresh;
   const uint64_t period = s->fastq ? 4 : 2;
   out->reads_processed = (total_lines + period - 1) / period;
   // Bloom::weight() divides two floats (utils/Bloom.cpp:191-203)

@@ -30,6 +30,7 @@ struct LoadCounters {
   unsigned long long kmers;       // k-mer occurrences streamed
   unsigned long long segments;    // "Unambiguous reads" (utils/Bloom.cpp:287)
   unsigned long long pending;     // occurrences that needed kernel B
+  unsigned long long fresh;       // occurrences NOT contained in bloo1 (went to bloo1)
   unsigned long long weight1, weight2;
 };
 
@@ -102,7 +103,7 @@ __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uin
 }
 
 template <int NH>
-__device__ __forceinline__ void load_body_B(const LoadArgs& a, uint64_t fwd, uint32_t t) {
+__device__ __forceinline__ bool load_body_B(const LoadArgs& a, uint64_t fwd, uint32_t t) {
   const int nh = NH ? NH : a.n_hash;
   uint64_t rc = revcomp(fwd, a.k);
   uint64_t c = canon(fwd, rc);
@@ -123,6 +124,7 @@ __device__ __forceinline__ void load_body_B(const LoadArgs& a, uint64_t fwd, uin
 #pragma unroll
   for (int i = 0; i < (NH ? NH : MAX_NHASH); i++)
     if (i < nh) atomicOr(reinterpret_cast<unsigned int*>(a.fused) + 2 * (pos[i] >> 5) + half, 1u << (pos[i] & 31));
+  return contained;
 }
 
 template <int NH>
@@ -169,12 +171,15 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_B_kernel(LoadArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * LOAD_THREADS + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * LOAD_THREADS) >> 5;
+  unsigned int n_fresh = 0;
   for (uint32_t w = warp; w < a.n_words; w += n_warps) {
     uint32_t pb = __ldg(a.pend + w);
     if (!((pb >> lane) & 1u)) continue;
     uint32_t p = (w << 5) + lane;
-    load_body_B<NH>(a, kmer_at(a.packed, p, a.k), a.base + p);
+    n_fresh += load_body_B<NH>(a, kmer_at(a.packed, p, a.k), a.base + p) ? 0u : 1u;
   }
+  for (int o = 16; o; o >>= 1) n_fresh += __shfl_xor_sync(0xffffffffu, n_fresh, o);
+  if (lane == 0 && n_fresh) atomicAdd(&a.ctr->fresh, (unsigned long long)n_fresh);
 }
 
 // Lines with several segments: getUnambiguousReads returns them LAST segment first
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_complex_kernel(LoadArgs a) 
       for (uint32_t p = ss + lane; p + a.k <= ee; p += 32) {
         uint64_t fwd = kmer_at(a.packed, p, a.k);
         if (PHASE == 0) load_body_A<0>(a, fwd, t0 + (p - ss));
-        else load_body_B<0>(a, fwd, t0 + (p - ss));
+        else if (!load_body_B<0>(a, fwd, t0 + (p - ss))) atomicAdd(&a.ctr->fresh, 1ull);
       }
     }
   }

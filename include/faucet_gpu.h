@@ -44,6 +44,7 @@ typedef struct {
 /* what load_two_filters prints (utils/Bloom.cpp:345-349) */
 typedef struct {
   uint64_t reads_processed, unambiguous_reads, kmers;
+  uint64_t fresh_kmers;    /* occurrences NOT found in bloo1 (they were added to bloo1, not bloo2) */
   double weight1, weight2; /* Bloom::weight() of bloo1 / bloo2 after the load */
 } faucet_load_stats;
 
