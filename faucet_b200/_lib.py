@@ -39,6 +39,11 @@ class LoadStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "parse_ms", "load_ms", "scan_ms", "stitch_ms", "d2h_ms", "total_ms")] + \
+               [(n, C.c_uint64) for n in ("kernel_launches", "stitch_rounds", "stitch_deferred")]
+
+
 _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
 _recpp = C.POINTER(C.POINTER(JunctionRec))
@@ -67,6 +72,8 @@ def _load():
     L.faucet_gpu_free.argtypes = [C.c_void_p]
     L.faucet_gpu_set_batch_bytes.argtypes = [C.c_size_t]
     L.faucet_gpu_set_epoch_limit.argtypes = [C.c_uint64]
+    L.faucet_gpu_set_tuning.argtypes = [C.c_char_p, C.c_uint64]
+    L.faucet_gpu_get_timings.argtypes = [C.POINTER(Timings)]
     vp = C.c_void_p
     L.faucet_session_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t]
     L.faucet_session_destroy.argtypes = [vp]
@@ -76,6 +83,8 @@ def _load():
     L.faucet_session_load.argtypes = [vp]
     L.faucet_session_scan_flags.argtypes = [vp]
     L.faucet_session_stitch.argtypes = [vp, C.c_int, C.c_int, _u64p]
+    L.faucet_session_stitch_begin.argtypes = [vp, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+    L.faucet_session_stitch_batch.argtypes = [vp]
     L.faucet_session_get_bloom.argtypes = [vp, _u8p, _u8p]
     L.faucet_session_set_bloom.argtypes = [vp, _u8p]
     L.faucet_session_get_junctions.argtypes = [vp, _recpp, _u64p, C.POINTER(ScanStats)]
@@ -114,6 +123,16 @@ def set_batch_bytes(n):
 
 def set_epoch_limit(n):
     _check(lib.faucet_gpu_set_epoch_limit(n))
+
+
+def set_tuning(name, value):
+    _check(lib.faucet_gpu_set_tuning(name.encode(), value))
+
+
+def timings():
+    t = Timings()
+    _check(lib.faucet_gpu_get_timings(C.byref(t)))
+    return {n: getattr(t, n) for n, _ in t._fields_}
 
 
 def geometry_from_reads(estimated_kmers, singletons, fp=0.04):

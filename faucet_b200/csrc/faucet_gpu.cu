@@ -13,7 +13,8 @@
 #include "load.cuh"
 #include "parse.cuh"
 #include "scan.cuh"
-#include "stitch_host.hpp"
+#include "pair_filter_host.hpp"
+#include "stitch.cuh"
 
 using namespace faucet;
 
@@ -26,6 +27,10 @@ struct Global {
   std::string err;
   size_t batch_bytes = (size_t)1 << 30;
   uint64_t epoch_limit = 0xfffffffeull;
+  unsigned long long table_cap0 = 1ull << 22;  // initial junction-table slots (grows by rehash)
+  int res_log2 = 24;                           // reservation table entries (u32 each)
+  uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048;
+  unsigned long long ext_cap0 = 1ull << 24;
   faucet_timings tim{};
   faucet_session* cached = nullptr;
 } g;
@@ -70,9 +75,31 @@ struct faucet_session {
   uint32_t* d_bloom = nullptr;  // plain bloo2
   uint32_t* d_bloom1 = nullptr; // plain bloo1 (only materialised on request)
   uint8_t* d_flags = nullptr;
-  uint8_t* h_flags = nullptr;   // pinned
-  uint8_t* h_text = nullptr;    // pinned copy of the batch text for the host stitch (device-resident runs)
-  HostStitch* stitch = nullptr;
+  // record table of the parsed batch (sequence line of record r = [seq_start[r], seq_end[r]))
+  uint32_t *d_seq_start = nullptr, *d_seq_end = nullptr;
+  size_t rec_cap = 0;
+  uint32_t n_recs = 0;          // records in the parsed batch
+  // pass 2 stitch: junction table + reservation state on the device (stitch.cuh)
+  bool stitching = false;
+  int paired = 0, no_cleaning = 1;
+  StitchState* d_st = nullptr;
+  unsigned long long *d_keys = nullptr, *d_jstamps = nullptr;
+  uint4* d_recs = nullptr;
+  unsigned long long tbl_cap = 0;
+  uint32_t* d_res = nullptr;
+  uint32_t* d_deferred[2] = {nullptr, nullptr};
+  uint32_t w_max = 0;
+  uint32_t* d_spf = nullptr;    // device copy of the short pair filter
+  uint8_t* h_spf = nullptr;     // caller's array (written back by stitch_end / get_junctions)
+  int spf_log2 = 0, spf_nh = 0;
+  unsigned long long* d_ext = nullptr;
+  unsigned long long ext_cap = 0;
+  std::vector<uint64_t> h_ext;
+  LongPairFilter lpf;
+  uint64_t rec_base = 0;        // global index of the first record of the current batch
+  std::vector<faucet_junction_rec> recs_out;
+  faucet_scan_stats sstats{};
+  int stitch_grid = 0;
   // bookkeeping
   uint64_t launches = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -130,7 +157,6 @@ int ensure_scan_buffers(faucet_session* s) {
   int rc;
   if (!s->d_bloom && (rc = dmalloc(&s->d_bloom, s->tai() / 32))) return rc;
   if (!s->d_flags && (rc = dmalloc(&s->d_flags, s->cap + TEXT_PAD))) return rc;
-  if (!s->h_flags) CU(cudaHostAlloc((void**)&s->h_flags, s->cap + TEXT_PAD, cudaHostAllocDefault));
   return 0;
 }
 
@@ -197,6 +223,29 @@ int faucet_gpu_set_epoch_limit(uint64_t stamps) {
   return 0;
 }
 int faucet_gpu_get_timings(faucet_timings* out) { *out = g.tim; return 0; }
+int faucet_gpu_set_tuning(const char* name, uint64_t value) {
+  std::string n(name ? name : "");
+  if (n == "table_cap0") {
+    if (value < 64 || (value & (value - 1))) return fail(FAUCET_E_ARG, "table_cap0 must be a power of two >= 64");
+    g.table_cap0 = value;
+  } else if (n == "res_log2") {
+    if (value < 8 || value > 30) return fail(FAUCET_E_ARG, "res_log2 out of range");
+    g.res_log2 = (int)value;
+  } else if (n == "stitch_w_max") {
+    if (value < 1 || value > (1u << 22)) return fail(FAUCET_E_ARG, "stitch_w_max out of range");
+    g.stitch_w_max = (uint32_t)value;
+  } else if (n == "stitch_w0") {
+    if (value < 1) return fail(FAUCET_E_ARG, "stitch_w0 out of range");
+    g.stitch_w0 = (uint32_t)value;
+  } else if (n == "ext_cap0") {
+    if (value < 64) return fail(FAUCET_E_ARG, "ext_cap0 out of range");
+    g.ext_cap0 = value;
+  } else {
+    return fail(FAUCET_E_ARG, "unknown tuning knob: " + n);
+  }
+  if (g.cached) { faucet_session_destroy(g.cached); g.cached = nullptr; }  // sessions size their buffers at creation
+  return 0;
+}
 void faucet_gpu_free(void* p) { free(p); }
 
 // ---- sessions ----------------------------------------------------------------------------------
@@ -219,7 +268,9 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   cudaEventCreate(&s->t1);
   size_t words = s->cap / 32 + TEXT_PAD;
   s->complex_cap = (uint32_t)(s->cap / 64 + 16);
-  if ((rc = dmalloc(&s->d_textbuf, s->cap + TEXT_PAD)) || (rc = dmalloc(&s->d_inval, words)) ||
+  s->rec_cap = s->cap / 4 + 16;  // a record is at least a header and a sequence line
+  if ((rc = dmalloc(&s->d_seq_start, s->rec_cap)) || (rc = dmalloc(&s->d_seq_end, s->rec_cap)) ||
+      (rc = dmalloc(&s->d_textbuf, s->cap + TEXT_PAD)) || (rc = dmalloc(&s->d_inval, words)) ||
       (rc = dmalloc(&s->d_packed, 2 * words)) || (rc = dmalloc(&s->d_skipA, words)) ||
       (rc = dmalloc(&s->d_chunk, s->cap / PARSE_CHUNK + 16)) || (rc = dmalloc(&s->d_pctr, 1)) ||
       (rc = dmalloc(&s->d_lctr, 1)) || (rc = dmalloc(&s->d_complex, s->complex_cap))) {
@@ -242,13 +293,12 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_textbuf); cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
-  cudaFree(s->d_bloom1); cudaFree(s->d_flags);
-  if (s->h_flags) cudaFreeHost(s->h_flags);
-  if (s->h_text) cudaFreeHost(s->h_text);
+  cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
+  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
+  cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);
   if (s->stream) cudaStreamDestroy(s->stream);
-  delete s->stitch;
   delete s;
 }
 
@@ -317,6 +367,10 @@ static int parse_batch(faucet_session* s, bool fastq, bool final_batch) {
   size_t words = (size_t)n_chunks * (PARSE_CHUNK / 32);
   CU(cudaMemsetAsync(s->d_pctr, 0, sizeof(ParseCounters), s->stream));
   CU(cudaMemsetAsync(s->d_skipA, 0, (words + 2) * 4, s->stream));
+  // records of this batch <= lines / period (+1 for a ragged tail)
+  const size_t rec_bound = std::min(s->rec_cap, s->n / (fastq ? 4 : 2) + 2);
+  CU(cudaMemsetAsync(s->d_seq_start, 0, rec_bound * 4, s->stream));
+  CU(cudaMemsetAsync(s->d_seq_end, 0, rec_bound * 4, s->stream));
   {
     KTimer kt(s, KT_PARSE);
     parse_count_kernel<<<n_chunks, PARSE_THREADS, 0, s->stream>>>(s->d_text, s->n, s->d_chunk);
@@ -325,6 +379,7 @@ static int parse_batch(faucet_session* s, bool fastq, bool final_batch) {
     a.text = s->d_text; a.n = s->n; a.inval = s->d_inval; a.packed = s->d_packed; a.skipA = s->d_skipA;
     a.chunk_prefix = s->d_chunk; a.ctr = s->d_pctr; a.complex_list = s->d_complex; a.complex_cap = s->complex_cap;
     a.period_mask = fastq ? 3 : 1; a.final_batch = final_batch ? 1 : 0; a.k = s->k;
+    a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.rec_shift = fastq ? 2 : 1; a.rec_cap = (uint32_t)rec_bound;
     parse_planes_kernel<<<n_chunks, PARSE_THREADS, 0, s->stream>>>(a);
     s->launches += 3;
   }
@@ -335,6 +390,19 @@ static int parse_batch(faucet_session* s, bool fastq, bool final_batch) {
   int rc = check_launch("parse");
   if (rc) return rc;
   if (s->h_pctr.complex_overflow) return fail(FAUCET_E_NOMEM, "too many multi-segment lines in one batch");
+  {  // records = header lines that belong to this batch (a ragged tail counts: std::getline semantics)
+    const uint64_t period = fastq ? 4 : 2;
+    uint64_t lines = s->h_pctr.total_newlines;
+    if (final_batch) {
+      uint8_t last = '\n';
+      if (s->n) CU(cudaMemcpy(&last, s->d_text + s->n - 1, 1, cudaMemcpyDeviceToHost));
+      if (s->n && last != '\n') lines++;
+      s->n_recs = (uint32_t)((lines + period - 1) / period);
+    } else {
+      s->n_recs = (uint32_t)(lines / period);
+    }
+    if (s->n_recs > rec_bound) return fail(FAUCET_E_NOMEM, "too many records in one batch");
+  }
   s->parsed = true;
   return 0;
 }
@@ -433,49 +501,214 @@ int faucet_session_scan_flags(faucet_session* s) {
   return check_launch("scan_flags");
 }
 
-int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_cleaning, uint8_t* short_pf,
-                                int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai,
-                                int lpf_n_hash) {
-  delete s->stitch;
-  s->stitch = new HostStitch(s->k, s->j, s->max_spacer, paired_ends != 0, no_cleaning != 0);
-  s->stitch->set_pair_filters(short_pf, spf_log2_tai, spf_n_hash, long_pf, lpf_log2_tai, lpf_n_hash);
+// ---- pass 2, stream-order part: GPU junction table (stitch.cuh) ------------------------------------
+
+static int stitch_alloc_table(faucet_session* s, unsigned long long cap) {
+  int rc;
+  if ((rc = dmalloc(&s->d_keys, cap + 1)) || (rc = dmalloc(&s->d_recs, cap + 1)) || (rc = dmalloc(&s->d_jstamps, cap + 1)))
+    return rc;
+  CU(cudaMemsetAsync(s->d_keys, 0xff, (cap + 1) * 8, s->stream));
+  CU(cudaMemsetAsync(s->d_recs, 0, (cap + 1) * 16, s->stream));
+  CU(cudaMemsetAsync(s->d_jstamps, 0, (cap + 1) * 8, s->stream));
+  s->tbl_cap = cap;
   return 0;
 }
 
-// host_text: the same bytes as the device batch (NULL => copied back from the device)
-int faucet_session_stitch_batch(faucet_session* s, const uint8_t* host_text, size_t valid_bytes) {
-  if (!s->stitch) return fail(FAUCET_E_STATE, "stitch_begin not called");
-  CU(cudaMemcpyAsync(s->h_flags, s->d_flags, s->n, cudaMemcpyDeviceToHost, s->stream));
-  if (!host_text) {
-    if (!s->h_text) CU(cudaHostAlloc((void**)&s->h_text, s->cap + TEXT_PAD, cudaHostAllocDefault));
-    CU(cudaMemcpyAsync(s->h_text, s->d_text, s->n, cudaMemcpyDeviceToHost, s->stream));
-    host_text = s->h_text;
-  }
+static int stitch_grow_table(faucet_session* s) {
+  unsigned long long *ok = s->d_keys, *os = s->d_jstamps;
+  uint4* orc = s->d_recs;
+  const unsigned long long ocap = s->tbl_cap;
+  s->d_keys = nullptr; s->d_recs = nullptr; s->d_jstamps = nullptr;
+  int rc = stitch_alloc_table(s, ocap * 2);
+  if (rc) return rc;
+  stitch_rehash_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(ok, orc, os, ocap, s->d_keys, s->d_recs, s->d_jstamps, s->tbl_cap);
+  s->launches++;
   CU(cudaStreamSynchronize(s->stream));
-  s->stitch->process(host_text, valid_bytes, s->h_flags, s->fastq);
+  cudaFree(ok); cudaFree(orc); cudaFree(os);
+  return check_launch("stitch_rehash");
+}
+
+int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_cleaning, uint8_t* short_pf,
+                                int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai,
+                                int lpf_n_hash) {
+  int rc;
+  s->paired = paired_ends; s->no_cleaning = no_cleaning;
+  if (!s->d_st && (rc = dmalloc(&s->d_st, 1))) return rc;
+  if (!s->d_keys) {
+    if ((rc = stitch_alloc_table(s, g.table_cap0))) return rc;
+  } else {  // a new scan starts from an empty JunctionMap
+    CU(cudaMemsetAsync(s->d_keys, 0xff, (s->tbl_cap + 1) * 8, s->stream));
+    CU(cudaMemsetAsync(s->d_recs, 0, (s->tbl_cap + 1) * 16, s->stream));
+  }
+  s->w_max = g.stitch_w_max;
+  if (!s->d_res) {
+    if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
+    CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+  }
+  for (int i = 0; i < 2; i++)
+    if (!s->d_deferred[i] && (rc = dmalloc(&s->d_deferred[i], s->w_max))) return rc;
+  CU(cudaMemsetAsync(s->d_st, 0, sizeof(StitchState), s->stream));
+  unsigned int w0 = std::min(g.stitch_w0, s->w_max);
+  CU(cudaMemcpyAsync(&s->d_st->W, &w0, 4, cudaMemcpyHostToDevice, s->stream));
+  // short pair filter: adds only (src/ReadScanner.cpp:208-225) => atomicOr on a device copy
+  cudaFree(s->d_spf); s->d_spf = nullptr; s->h_spf = nullptr;
+  if (short_pf && !no_cleaning) {
+    size_t words = ((size_t)1 << spf_log2_tai) / 32;
+    if (words == 0) words = 1;
+    if ((rc = dmalloc(&s->d_spf, words))) return rc;
+    CU(cudaMemcpyAsync(s->d_spf, short_pf, ((size_t)1 << spf_log2_tai) / 8, cudaMemcpyHostToDevice, s->stream));
+    s->h_spf = short_pf; s->spf_log2 = spf_log2_tai; s->spf_nh = spf_n_hash;
+  }
+  // long pair filter: sequential per mate pair => host, fed by the extension lists the kernel emits
+  s->lpf = LongPairFilter();
+  if (long_pf && paired_ends && !no_cleaning) {
+    s->lpf.init(long_pf, lpf_log2_tai, lpf_n_hash, s->k);
+    if (!s->d_ext) {
+      s->ext_cap = g.ext_cap0;
+      if ((rc = dmalloc(&s->d_ext, s->ext_cap))) return rc;
+    }
+  }
+  s->h_ext.clear();
+  s->rec_base = 0;
+  s->recs_out.clear();
+  std::memset(&s->sstats, 0, sizeof s->sstats);
+  if (!s->stitch_grid) {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stitch_kernel, STITCH_THREADS, 0));
+    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_kernel cannot be made resident");
+    s->stitch_grid = per_sm * g.sm_count;
+  }
+  s->stitching = true;
+  return 0;
+}
+
+// runs the stitch over the parsed + flagged batch that is resident in the session
+int faucet_session_stitch_batch(faucet_session* s) {
+  if (!s->stitching) return fail(FAUCET_E_STATE, "stitch_begin not called");
+  if (!s->parsed) return fail(FAUCET_E_STATE, "stitch_batch before parse");
+  const bool want_ext = s->lpf.enabled();
+  struct { unsigned int next, nd[2]; } z = {0, {0, 0}};
+  CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
+  s->h_ext.clear();
+  while (true) {
+    CU(cudaMemsetAsync(s->d_st->need, 0, sizeof(unsigned long long) * 2, s->stream));
+    StitchArgs a;
+    a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->d_flags;
+    a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
+    a.k = s->k; a.j = s->j; a.spacer = s->max_spacer; a.no_cleaning = s->no_cleaning; a.paired = s->paired;
+    a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
+    a.res = s->d_res; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
+    a.deferred[0] = s->d_deferred[0]; a.deferred[1] = s->d_deferred[1];
+    a.st = s->d_st;
+    a.spf = s->d_spf; a.spf_mask = s->d_spf ? ((1ull << s->spf_log2) - 1) : 0; a.spf_nh = s->spf_nh;
+    a.ext = want_ext ? s->d_ext : nullptr; a.ext_cap = s->ext_cap;
+    a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
+    void* params[] = {&a};
+    {
+      KTimer kt(s, KT_STITCH);
+      CU(cudaLaunchCooperativeKernel((void*)stitch_kernel, dim3(s->stitch_grid), dim3(STITCH_THREADS), params, 0, s->stream));
+      s->launches++;
+    }
+    unsigned int status = 0;
+    CU(cudaMemcpyAsync(&status, &s->d_st->status, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    int rc = check_launch("stitch");
+    if (rc) return rc;
+    if (status == ST_DONE) break;
+    // an aborted round leaves its reservations behind
+    CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+    if (status == ST_GROW_TABLE) {
+      if ((rc = stitch_grow_table(s))) return rc;
+    } else if (status == ST_DRAIN_EXT) {
+      unsigned long long used = 0;
+      CU(cudaMemcpy(&used, &s->d_st->ext_used, 8, cudaMemcpyDeviceToHost));
+      if (used == 0) {  // one round alone does not fit: a bigger buffer
+        cudaFree(s->d_ext); s->d_ext = nullptr;
+        s->ext_cap *= 2;
+        if ((rc = dmalloc(&s->d_ext, s->ext_cap))) return rc;
+      } else {
+        size_t at = s->h_ext.size();
+        s->h_ext.resize(at + used);
+        CU(cudaMemcpy(s->h_ext.data() + at, s->d_ext, used * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemsetAsync(&s->d_st->ext_used, 0, 8, s->stream));
+      }
+    } else {
+      return fail(FAUCET_E_CUDA, "stitch kernel returned an unknown status");
+    }
+  }
+  if (want_ext) {
+    unsigned long long used = 0;
+    CU(cudaMemcpy(&used, &s->d_st->ext_used, 8, cudaMemcpyDeviceToHost));
+    size_t at = s->h_ext.size();
+    s->h_ext.resize(at + used);
+    if (used) CU(cudaMemcpy(s->h_ext.data() + at, s->d_ext, used * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemsetAsync(&s->d_st->ext_used, 0, 8, s->stream));
+    s->lpf.process_batch(s->h_ext.data(), s->h_ext.size(), s->n_recs, s->rec_base);
+  }
+  s->rec_base += s->n_recs;
+  return 0;
+}
+
+// gathers the junction map (sorted into creation order) and the counters; writes the short pair
+// filter back to the caller's array
+static int stitch_finish(faucet_session* s) {
+  StitchState st;
+  CU(cudaMemcpyAsync(&st, s->d_st, sizeof st, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  const size_t n = (size_t)st.n_entries;
+  JunctionOut* d_out = nullptr;
+  unsigned long long* d_n = nullptr;
+  int rc;
+  if ((rc = dmalloc(&d_out, std::max<size_t>(1, n))) || (rc = dmalloc(&d_n, 1))) { cudaFree(d_out); return rc; }
+  CU(cudaMemsetAsync(d_n, 0, 8, s->stream));
+  stitch_collect_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(s->d_keys, s->d_recs, s->d_jstamps, s->tbl_cap, st.special, d_out, d_n);
+  s->launches++;
+  static_assert(sizeof(JunctionOut) == sizeof(faucet_junction_rec), "record layouts must agree");
+  s->recs_out.resize(n);
+  if (n) CU(cudaMemcpyAsync(s->recs_out.data(), d_out, n * sizeof(JunctionOut), cudaMemcpyDeviceToHost, s->stream));
+  if (s->h_spf) CU(cudaMemcpyAsync(s->h_spf, s->d_spf, ((size_t)1 << s->spf_log2) / 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(d_out); cudaFree(d_n);
+  if ((rc = check_launch("stitch_collect"))) return rc;
+  // creation order = (record index, n-th creation inside the record)
+  std::sort(s->recs_out.begin(), s->recs_out.end(),
+            [](const faucet_junction_rec& x, const faucet_junction_rec& y) { return x.creation_rank < y.creation_rank; });
+  for (size_t i = 0; i < n; i++) s->recs_out[i].creation_rank = i;
+  faucet_scan_stats& o = s->sstats;
+  o.n_junctions = n;
+  o.nb_jcheck_kmer = st.stats[SS_JCHECK]; o.nb_no_juncs = st.stats[SS_NOJUNC]; o.nb_processed = st.stats[SS_PROCESSED];
+  o.nb_skipped = st.stats[SS_SKIPPED]; o.reads_no_errors = st.stats[SS_NOERR]; o.unambiguous_reads = st.stats[SS_UNAMBIG];
+  o.reads_processed = s->rec_base;
+  g.tim.stitch_rounds = st.stats[SS_ROUNDS];
+  g.tim.stitch_deferred = st.stats[SS_DEFERRED];
   return 0;
 }
 
 int faucet_session_stitch(faucet_session* s, int paired_ends, int no_cleaning, uint64_t* n_junctions_out) {
   int rc = faucet_session_stitch_begin(s, paired_ends, no_cleaning, nullptr, 0, 0, nullptr, 0, 0);
   if (rc) return rc;
-  rc = faucet_session_stitch_batch(s, nullptr, s->n);
-  if (rc) return rc;
-  if (n_junctions_out) *n_junctions_out = s->stitch->records().size();
+  if ((rc = faucet_session_stitch_batch(s))) return rc;
+  if (n_junctions_out) {
+    unsigned long long n = 0;
+    CU(cudaMemcpy(&n, &s->d_st->n_entries, 8, cudaMemcpyDeviceToHost));
+    *n_junctions_out = n;
+  }
   return 0;
 }
 
 int faucet_session_get_junctions(faucet_session* s, faucet_junction_rec** recs_out, uint64_t* n_out,
                                  faucet_scan_stats* stats) {
-  if (!s->stitch) return fail(FAUCET_E_STATE, "no stitch has run in this session");
-  auto& r = s->stitch->records();
+  if (!s->stitching) return fail(FAUCET_E_STATE, "no stitch has run in this session");
+  int rc = stitch_finish(s);
+  if (rc) return rc;
+  auto& r = s->recs_out;
   if (recs_out) {
     *recs_out = (faucet_junction_rec*)malloc(std::max<size_t>(1, r.size()) * sizeof(faucet_junction_rec));
     if (!*recs_out) return fail(FAUCET_E_NOMEM, "malloc");
     if (!r.empty()) memcpy(*recs_out, r.data(), r.size() * sizeof(faucet_junction_rec));
   }
   if (n_out) *n_out = r.size();
-  if (stats) *stats = s->stitch->stats();
+  if (stats) *stats = s->sstats;
   return 0;
 }
 
@@ -561,14 +794,10 @@ int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, 
     return rc;
   uint64_t total_lines = 0;
   rc = for_each_batch(s, text, n, fastq != 0, &total_lines,
-                      [&](const uint8_t* host, size_t lead, size_t consumed, bool) {
+                      [&](const uint8_t*, size_t, size_t, bool) {
                         int r = faucet_session_scan_flags(s);
                         if (r) return r;
-                        // flags are indexed by device offsets = host offsets + lead
-                        CU(cudaMemcpyAsync(s->h_flags, s->d_flags + lead, consumed, cudaMemcpyDeviceToHost, s->stream));
-                        CU(cudaStreamSynchronize(s->stream));
-                        s->stitch->process(host, consumed, s->h_flags, s->fastq);
-                        return 0;
+                        return faucet_session_stitch_batch(s);
                       });
   if (rc) return rc;
   rc = faucet_session_get_junctions(s, recs_out, n_recs_out, stats);

@@ -115,6 +115,12 @@ struct ParseArgs {
   int period_mask;  // 3 for FASTQ (4-line records), 1 for FASTA
   int final_batch;
   int k;
+  // record table for the stitch: sequence line of record r = text[seq_start[r], seq_end[r])
+  // (both pre-zeroed by the caller: a record whose sequence line is missing reads as empty)
+  uint32_t* seq_start;
+  uint32_t* seq_end;
+  int rec_shift;    // 2 for FASTQ, 1 for FASTA
+  uint32_t rec_cap; // entries in seq_start / seq_end (records beyond it are dropped; the host checks the count)
 };
 
 // a thread that owns the FIRST non-ACGT byte of a sequence line checks whether the line holds two
@@ -200,9 +206,19 @@ parse_planes_kernel(ParseArgs a) {
     if (i < 16) pk0 |= code << (30 - 2 * i); else pk1 |= code << (30 - 2 * (i - 16));
     if (seq_line && !ok && c != '\n' && (size_t)i < lim) parse_check_complex(a, off + i);
     if (c == '\n' && (size_t)i < lim) {
+      if (seq_line && (line >> a.rec_shift) < a.rec_cap) a.seq_end[line >> a.rec_shift] = (uint32_t)(off + i);
       line++;
       if (!a.final_batch && (unsigned long long)line == complete && complete > 0) a.ctr->cut = off + i + 1;
+      if (((((line & pm) == 1u) && (unsigned long long)line < complete) || (unsigned long long)line == quirk) &&
+          (line >> a.rec_shift) < a.rec_cap)
+        a.seq_start[line >> a.rec_shift] = (uint32_t)(off + i + 1);
     }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.final_batch && a.n > 0 && a.text[a.n - 1] != '\n') {
+    // unterminated last line: it is either a sequence line or the re-used header (quirk); a quirk line
+    // that is the only line of the batch starts at offset 0, which the zero-fill already says
+    if ((quirk != ~0ull || (total_nl & pm) == 1u) && (total_nl >> a.rec_shift) < a.rec_cap)
+      a.seq_end[total_nl >> a.rec_shift] = (uint32_t)a.n;
   }
   a.inval[off >> 5] = inval;
   a.packed[off >> 4] = pk0;

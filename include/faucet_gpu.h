@@ -52,6 +52,7 @@ typedef struct {
 typedef struct {
   float h2d_ms, parse_ms, load_ms, scan_ms, stitch_ms, d2h_ms, total_ms;
   uint64_t kernel_launches;
+  uint64_t stitch_rounds, stitch_deferred; /* reservation rounds / deferred records of the last scan */
 } faucet_timings;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
@@ -105,6 +106,11 @@ void faucet_gpu_free(void* p);
 int faucet_gpu_set_batch_bytes(size_t bytes);
 int faucet_gpu_set_epoch_limit(uint64_t stamps);
 int faucet_gpu_get_timings(faucet_timings* out);
+/* knobs of the GPU junction stitch (tests shrink them to force table growth, deferrals and buffer
+ * drains): "table_cap0" initial junction-table slots (power of two), "res_log2" log2 of the
+ * reservation-table entries, "stitch_w0" / "stitch_w_max" initial / maximal records per round,
+ * "ext_cap0" u64 words of the extension-list buffer that feeds the long pair filter */
+int faucet_gpu_set_tuning(const char* name, uint64_t value);
 
 /* ---- device-resident stage API (bench.py "value": inputs already in HBM) ------------------
  * A session owns the device buffers for one (k, geometry, j, spacer) configuration. */
@@ -120,11 +126,12 @@ int faucet_session_load(faucet_session* s);                    /* pass 1 over th
 int faucet_session_scan_flags(faucet_session* s);              /* pass 2, order-free part */
 int faucet_session_stitch(faucet_session* s, int paired_ends, int no_cleaning,
                           uint64_t* n_junctions_out);          /* pass 2, stream-order part */
-/* multi-batch form of the stitch: begin once (pair filters may be NULL), then one call per batch */
+/* multi-batch form of the stitch: begin once (pair filters may be NULL), then one call per parsed and
+ * flagged batch; get_junctions gathers the map (and writes the short pair filter back) */
 int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_cleaning, uint8_t* short_pf,
                                 int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai,
                                 int lpf_n_hash);
-int faucet_session_stitch_batch(faucet_session* s, const uint8_t* host_text, size_t valid_bytes);
+int faucet_session_stitch_batch(faucet_session* s);
 int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_t total_lines);
 int faucet_session_set_profiling(faucet_session* s, int on);   /* per-kernel CUDA-event timing */
 int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* bloo1_out);

@@ -173,3 +173,64 @@ def test_session_stage_api(fb, oracle, small_fq):
     assert _strip(grecs) == _strip(orecs)
     assert s.launches > 0
     s.close()
+
+
+@pytest.mark.parametrize("knobs", [
+    {"table_cap0": 64},                                   # junction table grows by rehash many times
+    {"ext_cap0": 64},                                     # extension-list buffer drained / regrown mid-batch
+    {"res_log2": 8, "stitch_w0": 4096},                   # reservation collisions: most records get deferred
+    {"stitch_w0": 1, "stitch_w_max": 1},                  # one record per round == plain sequential order
+    {"stitch_w0": 32768, "stitch_w_max": 32768},          # window far larger than the genome supports
+    {"table_cap0": 256, "ext_cap0": 256, "res_log2": 10, "stitch_w0": 512},
+])
+def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs):
+    """whatever the round schedule of the GPU stitch (window, collisions, growth, drains), the junction
+    map, counters and pair filters equal the sequential oracle's"""
+    _, text = small_fq
+    k, j = 31, 1
+    lt, nh = _geom(oracle, 100000, 50000)
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    sg, lg = oracle.geometry_optimal(100000 // 20, 0.01), oracle.geometry_optimal(100000 // 10, 0.01)
+    ospf, olpf = np.zeros((1 << sg[0]) // 8, np.uint8), np.zeros((1 << lg[0]) // 8, np.uint8)
+    gspf, glpf = ospf.copy(), olpf.copy()
+    orecs, ost = oracle.scan(text, True, True, 0, k, j, 100, b2, lt, nh, ospf, sg, olpf, lg)
+    defaults = {"table_cap0": 1 << 22, "ext_cap0": 1 << 24, "res_log2": 24, "stitch_w0": 2048, "stitch_w_max": 1 << 15}
+    try:
+        for name, v in knobs.items():
+            fb.set_tuning(name, v)
+        fb.set_batch_bytes(700_000)  # several batches: the table and the mate carry live across them
+        grecs, gst = fb.scan_mem(text, True, True, 0, k, j, 100, b2, lt, nh, gspf, sg, glpf, lg)
+        tim = fb.timings()
+    finally:
+        for name, v in defaults.items():
+            fb.set_tuning(name, v)
+        fb.set_batch_bytes(1 << 30)
+    assert gst == ost
+    assert _strip(grecs) == _strip(orecs)
+    assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
+    assert tim["stitch_rounds"] > 0
+
+
+def test_stitch_repetitive_reads(fb, oracle, tmp_path_factory):
+    """every read drawn from a 2 kbp genome at 400x: nearly all records conflict with their neighbours"""
+    p, text = _dataset(tmp_path_factory, "rep.fq", genome=2000, cov=400, length=100, insert=300, seed=17, err=0.01)
+    k, lt, nh = 21, 18, 3
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    for j in (0, 1):
+        orecs, ost = oracle.scan(text, True, True, 1, k, j, 100, b2, lt, nh)
+        grecs, gst = fb.scan_mem(text, True, True, 1, k, j, 100, b2, lt, nh)
+        assert gst == ost and _strip(grecs) == _strip(orecs)
+
+
+def test_scan_k32_all_g_key(fb, oracle):
+    """k = 32: the all-'G' k-mer has the bit pattern of the table's empty marker"""
+    reads = [b"G" * 70, b"ACGT" * 5 + b"G" * 40 + b"TTGCA" * 4, b"C" * 70, b"G" * 50 + b"A" + b"G" * 40]
+    text = b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(reads * 3))
+    k, lt, nh = 32, 16, 3
+    _, b2, _ = oracle.load_two_filters(text, False, k, lt, nh)
+    g2, _, _ = fb.load_two_filters_mem(text, False, k, lt, nh)
+    assert np.array_equal(g2, b2)
+    for j in (0, 1):
+        orecs, ost = oracle.scan(text, False, False, 1, k, j, 100, b2, lt, nh)
+        grecs, gst = fb.scan_mem(text, False, False, 1, k, j, 100, b2, lt, nh)
+        assert gst == ost and _strip(grecs) == _strip(orecs)
