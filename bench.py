@@ -220,7 +220,9 @@ def run_ours(args, w):
     barrier()
     clk = clocks.stop()
     launches = sess.launches - launches0
-    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags")}
+    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch")}
+    sess.junctions()  # gathers the map once (not timed) so that the stitch round counters are published
+    stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith("stitch_r") or k_.startswith("stitch_d")}
     sess.set_profiling(False)
     lstats = sess.load_stats()
     b2, _ = sess.get_bloom()
@@ -275,14 +277,14 @@ def run_ours(args, w):
                        "parallelism": "replicated read sets, one per GPU" if world > 1 else "single GPU"},
             "e2e": {"value": kmers_all / (e2e_ms_all * 1e-3), "unit": "k-mers/s",
                     "h2d_bytes_per_step": 2 * n_text + bloo2.nbytes,
-                    "d2h_bytes_per_step": bloo2.nbytes + n_text + 32 * int(n_junc), "steps": e2e_steps},
+                    "d2h_bytes_per_step": bloo2.nbytes + 32 * int(n_junc), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                          "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms},
             "kernels_ms_per_step": {n: v[0] / args.steps for n, v in kernel_ms.items()},
-            "bloom_weight2": weight2, "contained_fraction": r_contained,
+            "bloom_weight2": weight2, "contained_fraction": r_contained, "stitch": stitch_info,
         }
         if args.cpu_baseline:
             kind, ck, times, sample = cpu_reference_sample(w, k, lt, nh, path, int(os.environ.get("FAUCET_REF_SAMPLE_READS", "60000")))
