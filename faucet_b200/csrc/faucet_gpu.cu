@@ -31,6 +31,7 @@ struct Global {
   int res_log2 = 24;                           // reservation table entries (u32 each)
   uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048;
   unsigned long long ext_cap0 = 1ull << 24;
+  size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
   faucet_timings tim{};
   faucet_session* cached = nullptr;
 } g;
@@ -237,6 +238,12 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "stitch_w0") {
     if (value < 1) return fail(FAUCET_E_ARG, "stitch_w0 out of range");
     g.stitch_w0 = (uint32_t)value;
+  } else if (n == "load_sub_bytes0") {
+    if (value < 32) return fail(FAUCET_E_ARG, "load_sub_bytes0 out of range");
+    g.load_sub_bytes0 = value;
+  } else if (n == "load_sub_bytes") {
+    if (value < 32) return fail(FAUCET_E_ARG, "load_sub_bytes out of range");
+    g.load_sub_bytes = value;
   } else if (n == "ext_cap0") {
     if (value < 64) return fail(FAUCET_E_ARG, "ext_cap0 out of range");
     g.ext_cap0 = value;
@@ -424,24 +431,36 @@ int faucet_session_load(faucet_session* s) {
   a.fused = s->d_fused; a.stamps = s->d_stamps; a.tai_mask = s->tai() - 1; a.base = s->stamp_base;
   a.k = s->k; a.n_hash = s->n_hash; a.ctr = s->d_lctr; a.text = s->d_text; a.complex_list = s->d_complex;
   a.n_complex = s->h_pctr.n_complex;
-  const int grid = g.sm_count * 8;
-  {
-    KTimer kt(s, KT_LOAD_A);
-    DISPATCH_NH(load_A_kernel, s->n_hash, grid, LOAD_THREADS, s->stream, a);
-    s->launches++;
-  }
-  if (a.n_complex) {
-    load_complex_kernel<0><<<std::min<uint32_t>(grid, (a.n_complex + 7) / 8), LOAD_THREADS, 0, s->stream>>>(a);
-    s->launches++;
-  }
-  {
-    KTimer kt(s, KT_LOAD_B);
-    DISPATCH_NH(load_B_kernel, s->n_hash, grid, LOAD_THREADS, s->stream, a);
-    s->launches++;
-  }
-  if (a.n_complex) {
-    load_complex_kernel<1><<<std::min<uint32_t>(grid, (a.n_complex + 7) / 8), LOAD_THREADS, 0, s->stream>>>(a);
-    s->launches++;
+  // Sub-batches: kernel A treats "all bits already in bloo1 when the sub-batch starts" as contained and
+  // only the rest touches the 4-byte-per-bit stamp array, so short early sub-batches (bloo1 fills
+  // fast) keep almost every k-mer of a deep-coverage stream off the stamps.  Any partition by start
+  // offset is exact: stamps are global and monotone (load.cuh).
+  const uint32_t sub0 = (uint32_t)std::max<size_t>(1, g.load_sub_bytes0 / 32), sub_max = (uint32_t)std::max<size_t>(sub0, g.load_sub_bytes / 32);
+  uint32_t sub = sub0;
+  for (uint32_t wb = 0; wb < a.n_words; ) {
+    a.w_begin = wb;
+    a.w_end = (uint32_t)std::min<uint64_t>((uint64_t)wb + sub, a.n_words);
+    const int grid = (int)std::min<uint32_t>(g.sm_count * 8, (a.w_end - a.w_begin + 7) / 8);
+    {
+      KTimer kt(s, KT_LOAD_A);
+      DISPATCH_NH(load_A_kernel, s->n_hash, grid, LOAD_THREADS, s->stream, a);
+      s->launches++;
+    }
+    if (a.n_complex) {
+      load_complex_kernel<0><<<std::min<uint32_t>(g.sm_count * 8, (a.n_complex + 7) / 8), LOAD_THREADS, 0, s->stream>>>(a);
+      s->launches++;
+    }
+    {
+      KTimer kt(s, KT_LOAD_B);
+      DISPATCH_NH(load_B_kernel, s->n_hash, grid, LOAD_THREADS, s->stream, a);
+      s->launches++;
+    }
+    if (a.n_complex) {
+      load_complex_kernel<1><<<std::min<uint32_t>(g.sm_count * 8, (a.n_complex + 7) / 8), LOAD_THREADS, 0, s->stream>>>(a);
+      s->launches++;
+    }
+    wb = a.w_end;
+    sub = std::min<uint64_t>((uint64_t)sub * 2, sub_max);
   }
   s->stamp_base += (uint32_t)s->n + 1;
   return check_launch("load");

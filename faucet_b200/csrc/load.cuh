@@ -40,6 +40,7 @@ struct LoadArgs {
   const uint32_t* skipA;
   uint32_t* pend;                 // 1 bit / byte offset
   uint32_t n_words;               // ceil(n / 32)
+  uint32_t w_begin, w_end;        // words of this sub-batch (see faucet_session_load)
   unsigned long long* fused;      // tai/32 words: low half bloo1, high half bloo2
   uint32_t* stamps;               // T[tai]
   uint64_t tai_mask;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_A_kernel(LoadArgs a) {
   const uint32_t n_warps = (gridDim.x * LOAD_THREADS) >> 5;
   const uint64_t kbits = a.k >= 32 ? 0xffffffffull : ((1ull << a.k) - 1ull);
   unsigned long long n_kmers = 0, n_segs = 0, n_pend = 0;
-  for (uint32_t w = warp; w < a.n_words; w += n_warps) {
+  for (uint32_t w = a.w_begin + warp; w < a.w_end; w += n_warps) {
     uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
     bool start_ok = (inval_window(lo, hi, lane) & kbits) == 0;
     if (!__any_sync(0xffffffffu, start_ok)) {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_B_kernel(LoadArgs a) {
   const uint32_t warp = (blockIdx.x * LOAD_THREADS + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * LOAD_THREADS) >> 5;
   unsigned int n_fresh = 0;
-  for (uint32_t w = warp; w < a.n_words; w += n_warps) {
+  for (uint32_t w = a.w_begin + warp; w < a.w_end; w += n_warps) {
     uint32_t pb = __ldg(a.pend + w);
     if (!((pb >> lane) & 1u)) continue;
     uint32_t p = (w << 5) + lane;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_complex_kernel(LoadArgs a) 
   unsigned long long n_kmers = 0, n_segs = 0;
   for (uint32_t li = warp; li < a.n_complex; li += n_warps) {
     const uint32_t s = a.complex_list[li].x, e = a.complex_list[li].y;
+    if ((s >> 5) < a.w_begin || (s >> 5) >= a.w_end) continue;  // a line belongs to the sub-batch of its first byte
     uint32_t q = s;
     while (q < e) {
       while (q < e && !nt_valid(a.text[q])) q++;

@@ -10,6 +10,16 @@
 // testForJunction is a pure function of (bloo2, oriented k-mer, real next nucleotide); the stitch
 // (which half-steps are actually visited, in stream order) consumes these flags and never touches
 // the Bloom filter again.
+//
+// Work shape.  A position with V set has 6 alternate extensions (3 per direction); ~w of them pass
+// the first Bloom probe, ~w^n pass all n, and only those need the depth-j check (4^j more queries).
+// Doing that per lane leaves ~6 of 32 lanes busy (measured), so the warp works in stages and
+// re-packs the survivors of each stage densely over its lanes through shared memory:
+//   stage 0  lane = position: k-mer, canonical form, V
+//   stage 1  lane = position, 6 rounds: alternate -> canonical -> hash0 -> first probe; survivors queued
+//   stage 2  lane = queued survivor: hash1, remaining probes; full members queued as j-check candidates
+//   stage 3  lane = (candidate, next nucleotide) for j = 1, lane = candidate (DFS) for j >= 2
+//   stage 4  lane = position: fold the per-alternate results in the reference's order
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,7 +30,9 @@
 namespace faucet {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int MAX_J = 4;  // JChecker scratch arrays hold 1000 k-mers => j <= 4 (utils/JChecker.cpp:93-94)
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_Q = 192;  // 32 positions x 6 alternates
+constexpr int MAX_J = 4;     // JChecker scratch arrays hold 1000 k-mers => j <= 4 (utils/JChecker.cpp:93-94)
 
 struct ScanArgs {
   const uint32_t* inval;
@@ -32,18 +44,23 @@ struct ScanArgs {
   uint8_t* flags;
 };
 
+__device__ __forceinline__ bool bloom_bit(const ScanArgs& a, uint64_t h) {
+  return (__ldg(a.bloom + (h >> 5)) >> (h & 31)) & 1u;
+}
+
 // Bloom::oldContains -> contains(h0,h1), utils/Bloom.h:162-173,242-258 (early exit on a clear bit)
 template <int NH>
 __device__ __forceinline__ bool bloom_contains(const ScanArgs& a, uint64_t x, uint64_t xrc) {
   const int nh = NH ? NH : a.n_hash;
   uint64_t c = canon(x, xrc);
   uint64_t h = hash0(c) & a.tai_mask;
+  if (!bloom_bit(a, h)) return false;
   uint64_t h1 = hash1(c) & a.tai_mask;
 #pragma unroll
-  for (int i = 0; i < (NH ? NH : MAX_NHASH); i++) {
+  for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {
     if (i >= nh) break;
-    if (!((__ldg(a.bloom + (h >> 5)) >> (h & 31)) & 1u)) return false;
     h = (h + h1) & a.tai_mask;
+    if (!bloom_bit(a, h)) return false;
   }
   return true;
 }
@@ -69,56 +86,147 @@ __device__ bool jcheck(const ScanArgs& a, uint64_t x, uint64_t xrc, uint64_t mas
   return false;
 }
 
-// testForJunction for the cursor whose oriented k-mer is `base` (revcomp `base_rc`) and whose real
-// next nucleotide is `real`; returns bit0 = junction, bits1-2 = alternates that reached the j-check
-template <int NH>
-__device__ __forceinline__ uint32_t test_for_junction(const ScanArgs& a, uint64_t base, uint64_t base_rc,
-                                                      uint32_t real, uint64_t mask) {
-  uint32_t cnt = 0;
-#pragma unroll
-  for (uint32_t c = 0; c < 4; c++) {
-    if (c == real) continue;
-    uint64_t y = ext_fwd(base, c, mask), yr = ext_rc(base_rc, c, a.k);
-    if (bloom_contains<NH>(a, y, yr)) {
-      cnt++;
-      if (jcheck<NH>(a, y, yr, mask)) return 1u | (cnt << 1);
-    }
-  }
-  return cnt << 1;
-}
+struct ScanQueue {  // per warp
+  unsigned long long canon[SCAN_Q];  // canonical form of the queued alternate
+  unsigned long long h0[SCAN_Q];     // its first probe position
+  uint8_t tag[SCAN_Q];               // bit 0: the canonical form IS the oriented k-mer
+  uint8_t res[SCAN_Q];               // bit 0: Bloom member (counted as j-checked), bit 1: passed the j-check
+  uint8_t cand[SCAN_Q];              // queue indices of the full members
+};
 
 template <int NH>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
+  __shared__ ScanQueue queues[SCAN_WARPS];
+  ScanQueue& q = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t warp = (blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * SCAN_THREADS) >> 5;
-  const uint64_t kbits = a.k >= 32 ? 0xffffffffull : ((1ull << a.k) - 1ull);
-  const uint64_t mask = kmer_mask(a.k);
+  const int nh = NH ? NH : a.n_hash;
+  const int k = a.k;
+  const uint64_t kbits = k >= 32 ? 0xffffffffull : ((1ull << k) - 1ull);
+  const uint64_t mask = kmer_mask(k);
   for (uint32_t w = warp; w < a.n_words; w += n_warps) {
-    uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
-    uint64_t win = inval_window(lo, hi, lane);
-    bool start_ok = (win & kbits) == 0;
+    const uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
+    const uint64_t win = inval_window(lo, hi, lane);
+    const bool start_ok = (win & kbits) == 0;
     if (!__any_sync(0xffffffffu, start_ok)) continue;
-    if (!start_ok) continue;
     const uint32_t p = (w << 5) + lane;
-    uint64_t fwd = kmer_at(a.packed, p, a.k);
-    uint64_t rc = revcomp(fwd, a.k);
-    uint32_t f = 0;
-    if (bloom_contains<NH>(a, fwd, rc)) {
-      f = 1;
-      // FORWARD half-step needs read[p+k]; BACKWARD needs read[p-1] (utils/ReadKmer.cpp:107-114)
-      bool has_next = !((win >> a.k) & 1ull);
-      bool has_prev = lane ? !((lo >> (lane - 1)) & 1u) : (w && !(__ldg(a.inval + w - 1) >> 31));
-      if (has_next) {
-        uint32_t r = test_for_junction<NH>(a, fwd, rc, code_at(a.packed, p + a.k), mask);
-        f |= (r & 1u) << 1 | (r >> 1) << 3;
+    // ---- stage 0
+    uint64_t fwd = 0, rc = 0;
+    bool V = false;
+    if (start_ok) {
+      fwd = kmer_at(a.packed, p, k);
+      rc = revcomp(fwd, k);
+      V = bloom_contains<NH>(a, fwd, rc);
+    }
+    // FORWARD half-step needs read[p+k]; BACKWARD needs read[p-1] (utils/ReadKmer.cpp:107-114)
+    const bool has_next = V && !((win >> k) & 1ull);
+    const bool has_prev = V && (lane ? !((lo >> (lane - 1)) & 1u) : (w && !(__ldg(a.inval + w - 1) >> 31)));
+    const uint32_t real_f = has_next ? code_at(a.packed, p + k) : 0u;
+    const uint32_t real_b = has_prev ? nt_comp(code_at(a.packed, p - 1)) : 0u;
+    // ---- stage 1: first probe of the six alternates (t = 0..2 FORWARD, 3..5 BACKWARD, nucleotide order)
+    uint32_t my_idx = 0;   // 6 x 5 bits... queue index does not fit: keep one byte per alternate in two words
+    uint32_t my_idx_hi = 0;
+    uint32_t survived = 0;  // bit t: alternate t is queued
+    int n1 = 0;
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+      const bool fdir = t < 3;
+      const bool act = fdir ? has_next : has_prev;
+      const uint32_t real = fdir ? real_f : real_b;
+      const uint32_t tt = fdir ? t : t - 3;
+      const uint32_t c = tt < real ? tt : tt + 1;  // the tt-th nucleotide that is not the real extension
+      bool hit = false;
+      uint64_t cn = 0, h = 0;
+      bool cn_is_y = false;
+      if (act) {
+        const uint64_t y = ext_fwd(fdir ? fwd : rc, c, mask), yr = ext_rc(fdir ? rc : fwd, c, k);
+        cn_is_y = y < yr;
+        cn = cn_is_y ? y : yr;
+        h = hash0(cn) & a.tai_mask;
+        hit = bloom_bit(a, h);
       }
-      if (has_prev) {
-        uint32_t r = test_for_junction<NH>(a, rc, fwd, nt_comp(code_at(a.packed, p - 1)), mask);
-        f |= (r & 1u) << 2 | (r >> 1) << 5;
+      const uint32_t b = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int e = n1 + __popc(b & lt_mask);
+        q.canon[e] = cn; q.h0[e] = h; q.tag[e] = cn_is_y ? 1 : 0;
+        survived |= 1u << t;
+        if (t < 4) my_idx |= (uint32_t)e << (8 * t); else my_idx_hi |= (uint32_t)e << (8 * (t - 4));
+      }
+      n1 += __popc(b);
+    }
+    __syncwarp();
+    // ---- stage 2: remaining probes of the survivors
+    int n2 = 0;
+    for (int base = 0; base < n1; base += 32) {
+      const int e = base + lane;
+      bool full = false;
+      if (e < n1) {
+        full = true;
+        if (nh > 1) {
+          const uint64_t h1 = hash1(q.canon[e]) & a.tai_mask;
+          uint64_t h = q.h0[e];
+#pragma unroll
+          for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {
+            if (i >= nh) break;
+            h = (h + h1) & a.tai_mask;
+            if (!bloom_bit(a, h)) { full = false; break; }
+          }
+        }
+        q.res[e] = full ? (a.j == 0 ? 3 : 1) : 0;
+      }
+      const uint32_t b = __ballot_sync(0xffffffffu, full);
+      if (full) q.cand[n2 + __popc(b & lt_mask)] = (uint8_t)e;
+      n2 += __popc(b);
+    }
+    __syncwarp();
+    // ---- stage 3: depth-j check of the full members (JChecker::jcheck)
+    if (a.j == 1) {
+      for (int base = 0; base < 4 * n2; base += 32) {
+        const int task = base + lane;
+        if (task < 4 * n2) {
+          const int e = q.cand[task >> 2];
+          const uint32_t c = task & 3;
+          const uint64_t cn = q.canon[e], cr = revcomp(cn, k);
+          const bool is_y = q.tag[e] & 1;
+          const uint64_t y = is_y ? cn : cr, yr = is_y ? cr : cn;
+          if (bloom_contains<NH>(a, ext_fwd(y, c, mask), ext_rc(yr, c, k))) q.res[e] = 3;
+        }
+      }
+    } else if (a.j > 1) {
+      for (int base = 0; base < n2; base += 32) {
+        const int ci = base + lane;
+        if (ci < n2) {
+          const int e = q.cand[ci];
+          const uint64_t cn = q.canon[e], cr = revcomp(cn, k);
+          const bool is_y = q.tag[e] & 1;
+          if (jcheck<NH>(a, is_y ? cn : cr, is_y ? cr : cn, mask)) q.res[e] = 3;
+        }
       }
     }
-    a.flags[p] = (uint8_t)f;
+    __syncwarp();
+    // ---- stage 4: testForJunction's early exit, in nucleotide order (src/ReadScanner.cpp:41-53)
+    if (start_ok) {
+      uint32_t f = V ? 1u : 0u;
+#pragma unroll
+      for (int d = 0; d < 2; d++) {
+        uint32_t cnt = 0, junc = 0;
+#pragma unroll
+        for (int tt = 0; tt < 3; tt++) {
+          const int t = 3 * d + tt;
+          if (!junc && ((survived >> t) & 1u)) {
+            const uint32_t e = t < 4 ? (my_idx >> (8 * t)) & 0xffu : (my_idx_hi >> (8 * (t - 4))) & 0xffu;
+            const uint32_t r = q.res[e];
+            cnt += r & 1u;
+            junc = (r >> 1) & 1u;
+          }
+        }
+        f |= d == 0 ? (junc << 1) | (cnt << 3) : (junc << 2) | (cnt << 5);
+      }
+      a.flags[p] = (uint8_t)f;
+    }
+    __syncwarp();  // the queues are reused by the next word
   }
 }
 

@@ -234,3 +234,21 @@ def test_scan_k32_all_g_key(fb, oracle):
         orecs, ost = oracle.scan(text, False, False, 1, k, j, 100, b2, lt, nh)
         grecs, gst = fb.scan_mem(text, False, False, 1, k, j, 100, b2, lt, nh)
         assert gst == ost and _strip(grecs) == _strip(orecs)
+
+
+@pytest.mark.parametrize("sub0,sub", [(32, 32 * 64), (4096, 4096), (1 << 20, 64 << 20)])
+def test_load_sub_batches(fb, oracle, small_fq, sub0, sub):
+    """the load pass may cut a batch into sub-batches of any size (even one 32-byte word) without changing a bit"""
+    _, text = small_fq
+    text = text[:text.find(b"\n@", 400_000) + 1]
+    lt, nh = _geom(oracle, 100000, 50000)
+    o1, o2, ost = oracle.load_two_filters(text, True, 31, lt, nh)
+    try:
+        fb.set_tuning("load_sub_bytes0", sub0)
+        fb.set_tuning("load_sub_bytes", sub)
+        g2, g1, gst = fb.load_two_filters_mem(text, True, 31, lt, nh, want_bloo1=True)
+    finally:
+        fb.set_tuning("load_sub_bytes0", 1 << 20)
+        fb.set_tuning("load_sub_bytes", 64 << 20)
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    assert gst.kmers == ost.kmers and gst.unambiguous_reads == ost.unambiguous_reads
