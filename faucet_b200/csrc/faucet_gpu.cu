@@ -25,7 +25,7 @@ struct Global {
   int device = 0;
   int sm_count = 148;
   std::string err;
-  size_t batch_bytes = (size_t)1 << 30;
+  size_t batch_bytes = (size_t)128 << 20;  // text bytes per pipelined device batch of the whole-pass entry points
   uint64_t epoch_limit = 0xfffffffeull;
   unsigned long long table_cap0 = 1ull << 22;  // initial junction-table slots (grows by rehash)
   int res_log2 = 24;                           // reservation table entries (u32 each)
@@ -57,9 +57,12 @@ struct faucet_session {
   int k = 0, log2_tai = 0, n_hash = 0, j = 0, max_spacer = 0;
   size_t cap = 0;  // bytes of text one batch may hold
   cudaStream_t stream = nullptr;
-  // batch text: d_textbuf has TAIL_MAX bytes of head-room so that a carried tail can be prepended
-  uint8_t* d_textbuf = nullptr;
-  uint8_t* d_text = nullptr;  // start of the current batch inside d_textbuf (16-byte aligned)
+  // batch text: two buffers so that the H2D copy of the next batch (copy stream) overlaps the kernels
+  // of the current one (whole-pass entry points); the second one is allocated on first use
+  uint8_t* d_textbufs[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  uint8_t* d_text = nullptr;  // the current batch
   size_t n = 0;               // bytes in the current batch
   bool fastq = false, parsed = false, final_batch = true;
   uint32_t *d_inval = nullptr, *d_packed = nullptr, *d_skipA = nullptr, *d_pend = nullptr, *d_chunk = nullptr;
@@ -277,7 +280,7 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   s->complex_cap = (uint32_t)(s->cap / 64 + 16);
   s->rec_cap = s->cap / 4 + 16;  // a record is at least a header and a sequence line
   if ((rc = dmalloc(&s->d_seq_start, s->rec_cap)) || (rc = dmalloc(&s->d_seq_end, s->rec_cap)) ||
-      (rc = dmalloc(&s->d_textbuf, s->cap + TEXT_PAD)) || (rc = dmalloc(&s->d_inval, words)) ||
+      (rc = dmalloc(&s->d_textbufs[0], s->cap + TEXT_PAD)) || (rc = dmalloc(&s->d_inval, words)) ||
       (rc = dmalloc(&s->d_packed, 2 * words)) || (rc = dmalloc(&s->d_skipA, words)) ||
       (rc = dmalloc(&s->d_chunk, s->cap / PARSE_CHUNK + 16)) || (rc = dmalloc(&s->d_pctr, 1)) ||
       (rc = dmalloc(&s->d_lctr, 1)) || (rc = dmalloc(&s->d_complex, s->complex_cap))) {
@@ -287,8 +290,11 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   cudaMemsetAsync(s->d_inval, 0xff, words * 4, s->stream);
   cudaMemsetAsync(s->d_packed, 0, 2 * words * 4, s->stream);
   cudaMemsetAsync(s->d_lctr, 0, sizeof(LoadCounters), s->stream);
-  cudaMemsetAsync(s->d_textbuf, '\n', s->cap + TEXT_PAD, s->stream);
-  s->d_text = s->d_textbuf + TAIL_MAX;
+  cudaMemsetAsync(s->d_textbufs[0], '\n', s->cap + TEXT_PAD, s->stream);
+  s->d_text = s->d_textbufs[0];
+  cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&s->ev_copied[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&s->ev_copied[1], cudaEventDisableTiming);
   *out = s;
   return 0;
 }
@@ -297,7 +303,9 @@ void faucet_session_destroy(faucet_session* s) {
   if (!s) return;
   if (s->stream) cudaStreamSynchronize(s->stream);
   drain_events(s);
-  cudaFree(s->d_textbuf); cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
+  if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+  for (int i = 0; i < 2; i++) { cudaFree(s->d_textbufs[i]); if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]); }
+  cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
   cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
@@ -337,24 +345,30 @@ int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64
   return 0;
 }
 
-// text placement: the batch starts `tail` bytes before d_textbuf+TAIL_MAX; the start is aligned down
-// to 16 bytes and the gap is filled with '#' (it lands on a header line, where it is inert).
-static int place_text(faucet_session* s, const void* text, size_t n, size_t tail, cudaMemcpyKind kind) {
-  if (n + tail > s->cap - TAIL_MAX + tail || tail > TAIL_MAX) return fail(FAUCET_E_ARG, "text larger than the session batch capacity");
-  uint8_t* start = s->d_textbuf + TAIL_MAX - tail;
-  uint8_t* aligned = (uint8_t*)((uintptr_t)start & ~(uintptr_t)15);
-  if (aligned != start) CU(cudaMemsetAsync(aligned, '#', start - aligned, s->stream));
-  if (n) CU(cudaMemcpyAsync(s->d_textbuf + TAIL_MAX, text, n, kind, s->stream));
-  s->d_text = aligned;
-  s->n = (start - aligned) + tail + n;
+// copies one batch of text into text buffer `buf` on stream `st` (not yet the current batch)
+static int stage_text(faucet_session* s, int buf, const void* text, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
+  if (n > s->cap - TAIL_MAX) return fail(FAUCET_E_ARG, "text larger than the session batch capacity");
+  if (!s->d_textbufs[buf]) {
+    int rc = dmalloc(&s->d_textbufs[buf], s->cap + TEXT_PAD);
+    if (rc) return rc;
+  }
+  uint8_t* dst = s->d_textbufs[buf];
+  if (n) CU(cudaMemcpyAsync(dst, text, n, kind, st));
   // bytes past the end must not look like bases of a previous, longer batch
-  CU(cudaMemsetAsync(s->d_text + s->n, '\n', TEXT_PAD, s->stream));
-  s->parsed = false;
+  CU(cudaMemsetAsync(dst + n, '\n', TEXT_PAD, st));
   return 0;
+}
+static void select_text(faucet_session* s, int buf, size_t n) {
+  s->d_text = s->d_textbufs[buf];
+  s->n = n;
+  s->parsed = false;
 }
 
 int faucet_session_set_text(faucet_session* s, const void* text, size_t n, int src_is_device) {
-  return place_text(s, text, n, 0, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+  int rc = stage_text(s, 0, text, n, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream);
+  if (rc) return rc;
+  select_text(s, 0, n);
+  return 0;
 }
 
 int faucet_session_reset_filters(faucet_session* s) {
@@ -750,32 +764,44 @@ static int get_session(faucet_session** out, int k, int log2_tai, int n_hash, in
   return 0;
 }
 
-// Feeds `text` through the session in batches cut at record boundaries.  `per_batch` runs the pass
-// on the parsed batch; consumed = bytes of the batch that belonged to complete records.
+// Feeds `text` through the session in batches cut at record boundaries.  `per_batch` runs the pass on
+// the parsed batch.  The H2D copy of batch i+1 is issued on the copy stream as soon as the parse of
+// batch i has told the host where batch i ends, so it overlaps the load / scan / stitch kernels of
+// batch i (the parse needs a host sync anyway, which also guarantees the other text buffer is free).
 template <class F>
 static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fastq, uint64_t* total_lines, F per_batch) {
   size_t off = 0;
   *total_lines = 0;
   const size_t room = s->cap - TAIL_MAX;
-  do {
-    size_t len = std::min(room, n - off);
-    bool final_batch = off + len == n;
-    int rc = place_text(s, text + off, len, 0, cudaMemcpyHostToDevice);
-    if (rc) return rc;
+  int buf = 0;
+  size_t len = std::min(room, n);
+  int rc = stage_text(s, buf, text, len, cudaMemcpyHostToDevice, s->copy_stream);
+  if (rc) return rc;
+  CU(cudaEventRecord(s->ev_copied[buf], s->copy_stream));
+  while (true) {
+    const bool final_batch = off + len == n;
+    CU(cudaStreamWaitEvent(s->stream, s->ev_copied[buf], 0));
+    select_text(s, buf, len);
     if ((rc = parse_batch(s, fastq, final_batch))) return rc;
     size_t consumed = len;
-    const size_t lead = s->n - len;  // '#' alignment bytes in front (0 here: no tail carried on the device)
     if (!final_batch) {
       if (s->h_pctr.cut == 0) return fail(FAUCET_E_ARG, "a single record does not fit in one batch");
-      consumed = (size_t)s->h_pctr.cut - lead;
+      consumed = (size_t)s->h_pctr.cut;
       uint64_t lines = s->h_pctr.total_newlines;
       *total_lines += lines - (lines % (fastq ? 4 : 2));
+      // next batch -> the other buffer, while this one is being processed
+      const size_t noff = off + consumed, nlen = std::min(room, n - noff);
+      if ((rc = stage_text(s, buf ^ 1, text + noff, nlen, cudaMemcpyHostToDevice, s->copy_stream))) return rc;
+      CU(cudaEventRecord(s->ev_copied[buf ^ 1], s->copy_stream));
     } else {
       *total_lines += s->h_pctr.total_newlines + ((len > 0 && text[off + len - 1] != '\n') ? 1 : 0);
     }
-    if ((rc = per_batch((const uint8_t*)text + off, lead, consumed, final_batch))) return rc;
+    if ((rc = per_batch((const uint8_t*)text + off, (size_t)0, consumed, final_batch))) return rc;
+    if (final_batch) break;
     off += consumed;
-  } while (off < n);
+    len = std::min(room, n - off);
+    buf ^= 1;
+  }
   return 0;
 }
 
