@@ -222,7 +222,7 @@ def run_ours(args, w):
     launches = sess.launches - launches0
     kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch")}
     sess.junctions()  # gathers the map once (not timed) so that the stitch round counters are published
-    stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith("stitch_r") or k_.startswith("stitch_d")}
+    stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith("stitch_")}
     sess.set_profiling(False)
     lstats = sess.load_stats()
     b2, _ = sess.get_bloom()

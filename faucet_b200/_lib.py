@@ -41,7 +41,8 @@ class LoadStats(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "parse_ms", "load_ms", "scan_ms", "stitch_ms", "d2h_ms", "total_ms")] + \
-               [(n, C.c_uint64) for n in ("kernel_launches", "stitch_rounds", "stitch_deferred")]
+               [(n, C.c_uint64) for n in ("kernel_launches", "stitch_rounds", "stitch_deferred")] + \
+               [("stitch_phase_ns", C.c_uint64 * 8)]
 
 
 _u8p = C.POINTER(C.c_uint8)
@@ -132,7 +133,7 @@ def set_tuning(name, value):
 def timings():
     t = Timings()
     _check(lib.faucet_gpu_get_timings(C.byref(t)))
-    return {n: getattr(t, n) for n, _ in t._fields_}
+    return {n: (list(getattr(t, n)) if n == "stitch_phase_ns" else getattr(t, n)) for n, _ in t._fields_}
 
 
 def geometry_from_reads(estimated_kmers, singletons, fp=0.04):

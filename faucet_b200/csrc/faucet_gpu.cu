@@ -29,7 +29,8 @@ struct Global {
   uint64_t epoch_limit = 0xfffffffeull;
   unsigned long long table_cap0 = 1ull << 22;  // initial junction-table slots (grows by rehash)
   int res_log2 = 24;                           // reservation table entries (u32 each)
-  uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048;
+  uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048, stitch_shrink_den = 4, stitch_grow_den = 10;
+  int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
   unsigned long long ext_cap0 = 1ull << 24;
   size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
   faucet_timings tim{};
@@ -88,11 +89,11 @@ struct faucet_session {
   int paired = 0, no_cleaning = 1;
   StitchState* d_st = nullptr;
   unsigned long long *d_keys = nullptr, *d_jstamps = nullptr;
-  uint4* d_recs = nullptr;
+  uint32_t* d_recs = nullptr;   // REC_WORDS u32 per slot
   unsigned long long tbl_cap = 0;
   uint32_t* d_res = nullptr;
   uint32_t* d_deferred[2] = {nullptr, nullptr};
-  uint32_t w_max = 0;
+  uint32_t w_max = 0, deferred_cap = 0;
   uint32_t* d_spf = nullptr;    // device copy of the short pair filter
   uint8_t* h_spf = nullptr;     // caller's array (written back by stitch_end / get_junctions)
   int spf_log2 = 0, spf_nh = 0;
@@ -104,6 +105,7 @@ struct faucet_session {
   std::vector<faucet_junction_rec> recs_out;
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
+  const void* stitch_fn = nullptr;
   // bookkeeping
   uint64_t launches = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -238,6 +240,12 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "stitch_w_max") {
     if (value < 1 || value > (1u << 22)) return fail(FAUCET_E_ARG, "stitch_w_max out of range");
     g.stitch_w_max = (uint32_t)value;
+  } else if (n == "stitch_shrink_den" || n == "stitch_grow_den") {
+    if (value < 1 || value > 1000) return fail(FAUCET_E_ARG, "stitch window thresholds out of range");
+    (n == "stitch_shrink_den" ? g.stitch_shrink_den : g.stitch_grow_den) = (uint32_t)value;
+  } else if (n == "stitch_blocks") {
+    if (value < 2 || value > 4) return fail(FAUCET_E_ARG, "stitch_blocks must be 2, 3 or 4");
+    g.stitch_blocks = (int)value;
   } else if (n == "stitch_w0") {
     if (value < 1) return fail(FAUCET_E_ARG, "stitch_w0 out of range");
     g.stitch_w0 = (uint32_t)value;
@@ -538,10 +546,10 @@ int faucet_session_scan_flags(faucet_session* s) {
 
 static int stitch_alloc_table(faucet_session* s, unsigned long long cap) {
   int rc;
-  if ((rc = dmalloc(&s->d_keys, cap + 1)) || (rc = dmalloc(&s->d_recs, cap + 1)) || (rc = dmalloc(&s->d_jstamps, cap + 1)))
+  if ((rc = dmalloc(&s->d_keys, cap + 1)) || (rc = dmalloc(&s->d_recs, (cap + 1) * REC_WORDS)) || (rc = dmalloc(&s->d_jstamps, cap + 1)))
     return rc;
   CU(cudaMemsetAsync(s->d_keys, 0xff, (cap + 1) * 8, s->stream));
-  CU(cudaMemsetAsync(s->d_recs, 0, (cap + 1) * 16, s->stream));
+  CU(cudaMemsetAsync(s->d_recs, 0, (cap + 1) * REC_WORDS * 4, s->stream));
   CU(cudaMemsetAsync(s->d_jstamps, 0, (cap + 1) * 8, s->stream));
   s->tbl_cap = cap;
   return 0;
@@ -549,7 +557,7 @@ static int stitch_alloc_table(faucet_session* s, unsigned long long cap) {
 
 static int stitch_grow_table(faucet_session* s) {
   unsigned long long *ok = s->d_keys, *os = s->d_jstamps;
-  uint4* orc = s->d_recs;
+  uint32_t* orc = s->d_recs;
   const unsigned long long ocap = s->tbl_cap;
   s->d_keys = nullptr; s->d_recs = nullptr; s->d_jstamps = nullptr;
   int rc = stitch_alloc_table(s, ocap * 2);
@@ -571,15 +579,31 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     if ((rc = stitch_alloc_table(s, g.table_cap0))) return rc;
   } else {  // a new scan starts from an empty JunctionMap
     CU(cudaMemsetAsync(s->d_keys, 0xff, (s->tbl_cap + 1) * 8, s->stream));
-    CU(cudaMemsetAsync(s->d_recs, 0, (s->tbl_cap + 1) * 16, s->stream));
+    CU(cudaMemsetAsync(s->d_recs, 0, (s->tbl_cap + 1) * REC_WORDS * 4, s->stream));
   }
   s->w_max = g.stitch_w_max;
+  if (!s->stitch_grid) {
+    int per_sm = 0;
+    const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
+    s->stitch_fn = g.stitch_blocks == 4 ? (const void*)stitch_kernel<4> : g.stitch_blocks == 3 ? (const void*)stitch_kernel<3> : (const void*)stitch_kernel<2>;
+    CU(cudaFuncSetAttribute(s->stitch_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->stitch_fn, STITCH_THREADS, smem));
+    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_kernel cannot be made resident");
+    s->stitch_grid = per_sm * g.sm_count;
+  }
+  // one record per warp per round
+  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * STITCH_WARPS);
   if (!s->d_res) {
     if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
   }
-  for (int i = 0; i < 2; i++)
-    if (!s->d_deferred[i] && (rc = dmalloc(&s->d_deferred[i], s->w_max))) return rc;
+  if (s->w_max > s->deferred_cap) {
+    for (int i = 0; i < 2; i++) {
+      cudaFree(s->d_deferred[i]); s->d_deferred[i] = nullptr;
+      if ((rc = dmalloc(&s->d_deferred[i], s->w_max))) return rc;
+    }
+    s->deferred_cap = s->w_max;
+  }
   CU(cudaMemsetAsync(s->d_st, 0, sizeof(StitchState), s->stream));
   unsigned int w0 = std::min(g.stitch_w0, s->w_max);
   CU(cudaMemcpyAsync(&s->d_st->W, &w0, 4, cudaMemcpyHostToDevice, s->stream));
@@ -605,12 +629,6 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   s->rec_base = 0;
   s->recs_out.clear();
   std::memset(&s->sstats, 0, sizeof s->sstats);
-  if (!s->stitch_grid) {
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stitch_kernel, STITCH_THREADS, 0));
-    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_kernel cannot be made resident");
-    s->stitch_grid = per_sm * g.sm_count;
-  }
   s->stitching = true;
   return 0;
 }
@@ -624,7 +642,6 @@ int faucet_session_stitch_batch(faucet_session* s) {
   CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
   s->h_ext.clear();
   while (true) {
-    CU(cudaMemsetAsync(s->d_st->need, 0, sizeof(unsigned long long) * 2, s->stream));
     StitchArgs a;
     a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->d_flags;
     a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
@@ -636,10 +653,12 @@ int faucet_session_stitch_batch(faucet_session* s) {
     a.spf = s->d_spf; a.spf_mask = s->d_spf ? ((1ull << s->spf_log2) - 1) : 0; a.spf_nh = s->spf_nh;
     a.ext = want_ext ? s->d_ext : nullptr; a.ext_cap = s->ext_cap;
     a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
+    a.shrink_den = g.stitch_shrink_den; a.grow_den = g.stitch_grow_den;
     void* params[] = {&a};
     {
       KTimer kt(s, KT_STITCH);
-      CU(cudaLaunchCooperativeKernel((void*)stitch_kernel, dim3(s->stitch_grid), dim3(STITCH_THREADS), params, 0, s->stream));
+      CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(STITCH_THREADS), params,
+                                     STITCH_WARPS * sizeof(WarpScratch), s->stream));
       s->launches++;
     }
     unsigned int status = 0;
@@ -714,6 +733,7 @@ static int stitch_finish(faucet_session* s) {
   o.reads_processed = s->rec_base;
   g.tim.stitch_rounds = st.stats[SS_ROUNDS];
   g.tim.stitch_deferred = st.stats[SS_DEFERRED];
+  for (int i = 0; i < 8; i++) g.tim.stitch_phase_ns[i] = st.stats[SS_T_PHASE1 + i];
   return 0;
 }
 

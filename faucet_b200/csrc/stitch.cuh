@@ -9,7 +9,7 @@
 //
 // Schedule ("windowed deterministic reservations"): a record can only read or
 // write junction keys that are k-mers (either orientation) of its own sequence line.  Rounds:
-//   phase 1  every record of the window (the deferred ones + the next W new ones, so every unexecuted
+//   phase 1  every record of the window (the deferred ones + the next new ones, so every unexecuted
 //            record with a smaller index is inside it) reserves its keys with atomicMin(record index);
 //   phase 2  a record executes iff it holds ALL its reservations, i.e. no earlier unexecuted record
 //            shares a key with it; otherwise it is deferred to the next round.
@@ -22,9 +22,18 @@
 // sharing is still detected (conservatively), with ~2/(k-s+2) reservations per k-mer instead of one.
 // The reservation array is a plain u32 table indexed by the minimizer hash (collisions only defer).
 //
-// The junction map itself is an open-addressing table in HBM (key = oriented k-mer, ReadKmer::getKmer;
-// 16-byte record = Junction's dist/cov/linked; 8-byte creation stamp = (record index, n-th creation in
-// that record)).  Sorting by stamp gives the reference's creation order.
+// Latency.  The junction table does not change during phase 1, and during phase 2 it only changes on
+// keys of executing records, which are private to them.  So a warp can look up EVERY half-step of its
+// line (table slot, stored skip distance, flag byte) in phase 1, with all loads in flight at once,
+// park the answers in shared memory across the grid barrier, and walk the line in phase 2 without
+// waiting on memory: the walk only re-reads what the line itself changed (tracked exactly).  Record
+// updates are commutative (dist = max, cov = count, linked = or) and are issued as fire-and-forget
+// atomics; what later records READ is ordered by the rounds.
+//
+// The junction map is an open-addressing table in HBM: key = oriented k-mer (ReadKmer::getKmer),
+// 64-byte record of u32 fields (dist[5], linked mask, cov[4] counts), 8-byte creation stamp =
+// (record index, n-th creation in that record).  Sorting by stamp gives the reference's creation
+// order; cov saturates at 255 when the map is collected (utils/Junction.cpp:59-67).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -41,16 +50,22 @@ constexpr int STITCH_THREADS = 256;
 constexpr int STITCH_WARPS = STITCH_THREADS / 32;
 constexpr unsigned long long KEY_EMPTY = ~0ull;
 constexpr uint32_t RES_FREE = 0xffffffffu;
-constexpr int EXT_STAGE = 32;  // staged real-extension k-mers per warp before a chunk is flushed
+constexpr int EXT_STAGE = 32;   // staged real-extension k-mers per warp before a chunk is flushed
+constexpr int POS_CAP = 256;    // k-mer positions per line served from shared memory (longer lines: direct path)
+constexpr int RES_CAP = 96;     // reservation slots per line kept in shared memory
+constexpr int VIS_CAP = 32;     // junction slots a line touched (beyond it every skip distance is re-read)
+constexpr int REC_WORDS = 16;   // u32 per junction record
+enum { REC_DIST = 0, REC_LINK = 5, REC_COV = 6 };
 
 enum { ST_DONE = 0, ST_GROW_TABLE = 1, ST_DRAIN_EXT = 2 };
-enum { SS_JCHECK = 0, SS_NOJUNC, SS_PROCESSED, SS_SKIPPED, SS_NOERR, SS_UNAMBIG, SS_ROUNDS, SS_DEFERRED, SS_COUNT };
+enum { SS_JCHECK = 0, SS_NOJUNC, SS_PROCESSED, SS_SKIPPED, SS_NOERR, SS_UNAMBIG, SS_ROUNDS, SS_DEFERRED,
+       SS_T_PHASE1, SS_T_SYNC1, SS_T_PHASE2, SS_T_SYNC2, SS_T_P1A, SS_T_P1B, SS_T_P1C, SS_T_P2A, SS_COUNT };  // SS_T_*: ns seen by warp 0 of the grid
 
 struct StitchState {             // device-resident; survives kernel launches and batches
   unsigned long long n_entries;  // occupied slots of the junction table
   unsigned long long stats[SS_COUNT];
   unsigned long long ext_used;   // u64 words used in the ext buffer
-  unsigned long long need[2];    // upper bound of junction events of the records reserved this round
+  unsigned long long max_need;   // upper bound of the junction events ONE record can cause (2 x longest line + 2)
   unsigned int next;             // next new record of the batch
   unsigned int nd[2];            // deferred-record counts, double-buffered by round parity
   unsigned int W;                // window size (adapts to the deferral rate)
@@ -70,9 +85,9 @@ struct StitchArgs {
   int k, j, spacer;
   int no_cleaning, paired;
   unsigned long long* keys;      // cap + 1 entries (the last one is the home of the KEY_EMPTY k-mer)
-  uint4* recs;
+  uint32_t* recs;                // REC_WORDS u32 per slot
   unsigned long long* stamps;
-  unsigned long long cap;        // power of two
+  unsigned long long cap;        // power of two, < 2^31
   uint32_t* res;                 // reservation table
   uint32_t res_mask;
   uint32_t* deferred[2];         // w_max entries each
@@ -82,9 +97,28 @@ struct StitchArgs {
   int spf_nh;
   unsigned long long* ext;       // real-extension chunks for the host-side long pair filter (NULL: none)
   unsigned long long ext_cap;
-  uint32_t w_min, w_max;
+  uint32_t w_min, w_max;         // w_max <= warps of the grid: one record per warp per round
+  uint32_t shrink_den, grow_den; // window halves when deferred > win/shrink_den, doubles when < win/grow_den
 };
 
+struct WarpScratch {             // shared memory of one warp; filled in phase 1, consumed in phase 2
+  unsigned long long kmer[POS_CAP];   // forward k-mer of every position of the line
+  int slot[2 * POS_CAP];              // table slot of the key at half-step 2*pos+dir, -1 = not a junction
+  uint8_t hop[2 * POS_CAP];           // stored dist[fwdIdx] of that junction when the round started
+  uint8_t flag[POS_CAP];              // scan_flags byte of the position
+  uint32_t pk[24];                    // the line's words of the 2-bit plane, from word ls>>4
+  uint32_t inv[12];                   // the line's words of the validity plane, from word ls>>5
+  uint32_t reskey[RES_CAP];           // reservation slots of the line
+  int visited[VIS_CAP];               // slots of the junctions this line has touched
+  unsigned long long stage[EXT_STAGE];
+  unsigned long long st[SS_COUNT];    // counters of this warp (lane 0), flushed when the kernel ends
+};
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
   return x;
@@ -94,9 +128,26 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
+// plane words either through the read-only path (global planes) or from the warp's shared copy
+template <bool SH>
+__device__ __forceinline__ uint32_t ldw(const uint32_t* p) { return SH ? *p : __ldg(p); }
+template <bool SH>
+__device__ __forceinline__ uint64_t kmer_at_t(const uint32_t* packed, uint32_t p, int k) {
+  const uint32_t w = p >> 4, o = 2 * (p & 15);
+  const uint64_t hi = ((uint64_t)ldw<SH>(packed + w) << 32) | ldw<SH>(packed + w + 1);
+  const uint64_t lo = (uint64_t)ldw<SH>(packed + w + 2) << 32;
+  const uint64_t x = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+  return x >> (64 - 2 * k);
+}
+template <bool SH>
+__device__ __forceinline__ uint32_t code_at_t(const uint32_t* packed, uint32_t p) {
+  return (ldw<SH>(packed + (p >> 4)) >> (30 - 2 * (p & 15))) & 3u;
+}
+
 // h(canonical s-mer starting at byte offset q), s <= 16
-__device__ __forceinline__ uint32_t smer_hash(const uint32_t* __restrict__ packed, uint32_t q, int s) {
-  uint32_t w0 = __ldg(packed + (q >> 4)), w1 = __ldg(packed + (q >> 4) + 1);
+template <bool SH>
+__device__ __forceinline__ uint32_t smer_hash(const uint32_t* packed, uint32_t q, int s) {
+  uint32_t w0 = ldw<SH>(packed + (q >> 4)), w1 = ldw<SH>(packed + (q >> 4) + 1);
   uint32_t x = __funnelshift_l(w1, w0, 2 * (q & 15)) >> (32 - 2 * s);
   uint32_t r = __brev(x << (32 - 2 * s));                       // reversed bit order, low-aligned
   r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);      // un-swap inside the 2-bit groups
@@ -104,93 +155,108 @@ __device__ __forceinline__ uint32_t smer_hash(const uint32_t* __restrict__ packe
   return mix32(x < r ? x : r);
 }
 
-// One warp walks the minimizers of line [ls, ls+len) and calls f(slot) once per run of equal values.
-// MODE 0: reserve, 1: check (returns false on a foreign reservation), 2: release own reservations.
-template <int MODE>
-__device__ bool line_reservations(const StitchArgs& a, uint32_t ls, uint32_t len, uint32_t rec, int lane) {
+// value at position lane+d of the 64-entry sequence (x0 = entries 0..31, x1 = entries 32..63)
+__device__ __forceinline__ uint32_t shift64(uint32_t x0, uint32_t x1, int d, int lane) {
+  const int src = (lane + d) & 31;
+  const uint32_t a = __shfl_sync(0xffffffffu, x0, src), b = __shfl_sync(0xffffffffu, x1, src);
+  return lane + d < 32 ? a : b;
+}
+
+// One warp walks the minimizers of line [ls, ls+len): one reservation slot per run of equal values.
+// MODE 0: reserve with atomicMin and remember the slots in `keep` (*n_keep > RES_CAP: did not fit);
+// MODE 1: check (false on a foreign reservation); MODE 2: release own reservations.
+template <int MODE, bool SH>
+__device__ bool line_reservations(const StitchArgs& a, const uint32_t* packed, uint32_t ls, uint32_t len, uint32_t rec,
+                                  int lane, uint32_t* keep, int* n_keep) {
   const int k = a.k, s = k < 16 ? k : 16, w = k - s + 1;
+  if (MODE == 0) *n_keep = 0;
   if (len < (uint32_t)k) return true;
   const uint32_t nk = len - k + 1, ns = len - s + 1;
+  int lg = 0;
+  while ((2 << lg) <= w) lg++;  // 2^lg <= w < 2^(lg+1)
   bool ok = true;
-  uint32_t g0 = lane < (int)ns ? smer_hash(a.packed, ls + lane, s) : 0xffffffffu;
+  int nkeep = 0;
+  uint32_t g0 = lane < (int)ns ? smer_hash<SH>(packed, ls + lane, s) : 0xffffffffu;
   uint32_t prev_last = 0;  // minimizer of the last position of the previous chunk
   for (uint32_t base = 0; base < nk; base += 32) {
-    uint32_t q1 = base + 32 + lane;
-    uint32_t g1 = q1 < ns ? smer_hash(a.packed, ls + q1, s) : 0xffffffffu;
-    uint32_t m = 0xffffffffu;
-    for (int t = 0; t < w; t++) {
-      int src = (lane + t) & 31;
-      uint32_t v0 = __shfl_sync(0xffffffffu, g0, src), v1 = __shfl_sync(0xffffffffu, g1, src);
-      uint32_t v = lane + t < 32 ? v0 : v1;
-      m = v < m ? v : m;
+    const uint32_t q1 = base + 32 + lane;
+    const uint32_t g1 = q1 < ns ? smer_hash<SH>(packed, ls + q1, s) : 0xffffffffu;
+    // sliding minimum of width w by doubling: m_(2d)[p] = min(m_d[p], m_d[p+d])
+    uint32_t x0 = g0, x1 = g1;
+    for (int d = 1; d < (1 << lg); d <<= 1) {
+      const uint32_t y0 = shift64(x0, x1, d, lane);
+      uint32_t y1 = __shfl_sync(0xffffffffu, x1, (lane + d) & 31);
+      if (lane + d >= 32) y1 = 0xffffffffu;
+      x0 = x0 < y0 ? x0 : y0;
+      x1 = x1 < y1 ? x1 : y1;
+    }
+    uint32_t m = x0;
+    if (w > (1 << lg)) {
+      const uint32_t y = shift64(x0, x1, w - (1 << lg), lane);
+      m = m < y ? m : y;
     }
     uint32_t left = __shfl_up_sync(0xffffffffu, m, 1);
     if (lane == 0) left = prev_last;
-    bool active = base + lane < nk && (base + lane == 0 || m != left);
-    if (active) {
-      uint32_t* slot = a.res + (m & a.res_mask);
-      if (MODE == 0) atomicMin(slot, rec);
-      if (MODE == 1 && __ldcg(slot) != rec) ok = false;
-      if (MODE == 2 && __ldcg(slot) == rec) __stcg(slot, RES_FREE);
+    const bool active = base + lane < nk && (base + lane == 0 || m != left);
+    uint32_t* slot = a.res + (m & a.res_mask);
+    if (MODE == 0) {
+      if (active) atomicMin(slot, rec);
+      const uint32_t b = __ballot_sync(0xffffffffu, active);
+      const int at = nkeep + __popc(b & ((1u << lane) - 1u));
+      if (active && at < RES_CAP) keep[at] = m & a.res_mask;
+      nkeep += __popc(b);
     }
+    if (MODE == 1 && active && __ldcg(slot) != rec) ok = false;
+    if (MODE == 2 && active && __ldcg(slot) == rec) __stcg(slot, RES_FREE);
     prev_last = __shfl_sync(0xffffffffu, m, 31);
     g0 = g1;
   }
+  if (MODE == 0) *n_keep = nkeep;
   return MODE == 1 ? __all_sync(0xffffffffu, ok) : true;
 }
 
 // ---- junction table -----------------------------------------------------------------------------
-__device__ __forceinline__ long long tbl_find(const StitchArgs& a, uint64_t key) {
-  if (key == KEY_EMPTY) return __ldcg(&a.st->special) ? (long long)a.cap : -1;
+__device__ __forceinline__ int tbl_find(const StitchArgs& a, uint64_t key) {
+  if (key == KEY_EMPTY) return __ldcg(&a.st->special) ? (int)a.cap : -1;
   uint64_t h = mix64(key) & (a.cap - 1);
   while (true) {
     unsigned long long kk = __ldcg(a.keys + h);
-    if (kk == key) return (long long)h;
+    if (kk == key) return (int)h;
     if (kk == KEY_EMPTY) return -1;
     h = (h + 1) & (a.cap - 1);
   }
 }
 // one thread; returns the slot and whether the key was created (JunctionMap::createJunction, zeroed record)
-__device__ __forceinline__ long long tbl_insert(const StitchArgs& a, uint64_t key, bool* created) {
+__device__ __forceinline__ int tbl_insert(const StitchArgs& a, uint64_t key, bool* created) {
   if (key == KEY_EMPTY) {
     *created = atomicExch(&a.st->special, 1u) == 0u;
     if (*created) { a.keys[a.cap] = key; atomicAdd(&a.st->n_entries, 1ull); }
-    return (long long)a.cap;
+    return (int)a.cap;
   }
   uint64_t h = mix64(key) & (a.cap - 1);
   while (true) {
     unsigned long long old = atomicCAS(a.keys + h, KEY_EMPTY, (unsigned long long)key);
-    if (old == KEY_EMPTY) { *created = true; atomicAdd(&a.st->n_entries, 1ull); return (long long)h; }
-    if (old == key) { *created = false; return (long long)h; }
+    if (old == KEY_EMPTY) { *created = true; atomicAdd(&a.st->n_entries, 1ull); return (int)h; }
+    if (old == key) { *created = false; return (int)h; }
     h = (h + 1) & (a.cap - 1);
   }
 }
-
-// 16-byte record image: bytes 0-4 dist, 5-8 cov, 9-13 linked (utils/Junction.h:12-19)
-struct RecImg {
-  uint32_t w[4];
-  __device__ __forceinline__ uint32_t get(int b) const { return (w[b >> 2] >> (8 * (b & 3))) & 0xffu; }
-  __device__ __forceinline__ void set(int b, uint32_t v) {
-    w[b >> 2] = (w[b >> 2] & ~(0xffu << (8 * (b & 3)))) | (v << (8 * (b & 3)));
-  }
-  // Junction::update: dist = max(dist, (unsigned char)length)   (utils/Junction.cpp:69-71 + u8 narrowing at the call)
-  __device__ __forceinline__ void update(int idx, int length) {
-    uint32_t l = (uint32_t)length & 0xffu;
-    if (l > get(idx)) set(idx, l);
-  }
-  __device__ __forceinline__ void add_cov(int nt) {  // Junction::addCoverage, saturating (utils/Junction.cpp:59-67)
-    uint32_t c = get(5 + nt);
-    if (c != 255) set(5 + nt, c + 1);
-  }
-  __device__ __forceinline__ void link(int idx) { set(9 + idx, 1); }
-};
-__device__ __forceinline__ RecImg rec_load(const StitchArgs& a, long long slot) {
-  uint4 v = __ldcg(a.recs + slot);
-  RecImg r; r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-  return r;
+__device__ __forceinline__ uint32_t* rec_field(const StitchArgs& a, int slot, int f) {
+  return a.recs + (size_t)slot * REC_WORDS + f;
 }
-__device__ __forceinline__ void rec_store(const StitchArgs& a, long long slot, const RecImg& r) {
-  __stcg(a.recs + slot, make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]));
+// Junction::update: dist = max(dist, (unsigned char)length)  (utils/Junction.cpp:69-71; u8 narrowing at the call)
+__device__ __forceinline__ void rec_update(const StitchArgs& a, int slot, int idx, int length) {
+  atomicMax(rec_field(a, slot, REC_DIST + idx), (uint32_t)length & 0xffu);
+}
+__device__ __forceinline__ void rec_link(const StitchArgs& a, int slot, int idx) {
+  atomicOr(rec_field(a, slot, REC_LINK), 1u << idx);
+}
+__device__ __forceinline__ void rec_add_cov(const StitchArgs& a, int slot, int nt) {
+  atomicAdd(rec_field(a, slot, REC_COV + nt), 1u);
+}
+// the current dist[idx], ordered after this thread's own atomics on the same word
+__device__ __forceinline__ uint32_t rec_dist_now(const StitchArgs& a, int slot, int idx) {
+  return atomicMax(rec_field(a, slot, REC_DIST + idx), 0u);
 }
 
 // Bloom::addPair on the device copy of the short pair filter (utils/Bloom.cpp:127-140); adds commute
@@ -204,9 +270,15 @@ __device__ void spf_add_pair(const StitchArgs& a, uint64_t k1, uint64_t k2) {
 }
 
 struct WarpCtx {
-  unsigned long long st[SS_COUNT];  // lane 0 only
   unsigned long long stamp;         // next creation stamp of the current record
-  unsigned long long* stage;        // shared staging area of this warp (EXT_STAGE entries)
+  WarpScratch* S;
+  uint32_t ls;                      // byte offset of the current line
+  const uint32_t* pk;               // 2-bit plane as the walk sees it (shared copy or global) ...
+  uint32_t pk_base;                 // ... and the byte offset of its word 0
+  const uint32_t* inv;
+  uint32_t inv_base;
+  int n_pos;                        // k-mer positions of the line held in S (0: direct path)
+  int n_vis;                        // entries of S->visited (> VIS_CAP: overflowed)
   uint32_t n_stage, part, rec;
 };
 
@@ -218,33 +290,56 @@ __device__ void ext_flush(const StitchArgs& a, WarpCtx& c, int lane) {
   off = __shfl_sync(0xffffffffu, off, 0);
   if (lane == 0) a.ext[off] = ((unsigned long long)c.rec << 32) | ((unsigned long long)(c.part & 0xffffu) << 16) | n;
   __syncwarp();
-  if (lane < (int)n) a.ext[off + 1 + lane] = c.stage[lane];
+  if (lane < (int)n) a.ext[off + 1 + lane] = c.S->stage[lane];
   __syncwarp();
   c.n_stage = 0;
   c.part++;
 }
 
-// scan_forward (src/ReadScanner.cpp:112-231) on the valid sub-read at byte offset s0, `len` bases
+// has this line already touched `slot`?  (then the skip distance parked in phase 1 may be stale)
+__device__ __forceinline__ bool line_visited(const WarpCtx& c, int slot, int lane) {
+  if (c.n_vis > VIS_CAP) return true;
+  const bool hit = lane < c.n_vis && c.S->visited[lane] == slot;
+  return __any_sync(0xffffffffu, hit);
+}
+__device__ __forceinline__ void line_visit(WarpCtx& c, int slot, int lane) {
+  if (c.n_vis < VIS_CAP) { if (lane == 0) c.S->visited[c.n_vis] = slot; }
+  c.n_vis++;
+  __syncwarp();
+}
+// a key this line just created: every other half-step of the line with that key must now see it
+__device__ __forceinline__ void line_publish(const StitchArgs& a, WarpCtx& c, uint64_t key, int slot, int lane) {
+  for (int pos = lane; pos < c.n_pos; pos += 32) {
+    const uint64_t f = c.S->kmer[pos];
+    if (f == key) c.S->slot[2 * pos + 1] = slot;
+    if (revcomp(f, a.k) == key) c.S->slot[2 * pos] = slot;
+  }
+  __syncwarp();
+}
+
+// scan_forward (src/ReadScanner.cpp:112-231) on the valid sub-read at byte offset s0, `len` bases.
+// FAST: the line's lookups were parked in shared memory in phase 1 (c.S, index = s0 - c.ls + pos).
+template <bool FAST>
 __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int len, int lane) {
   const int k = a.k, j = a.j;
   const uint64_t mask = kmer_mask(k);
+  const int rel = (int)(s0 - c.ls);
   const int tested_end = 2 * len - 2 * k + 1 - 2 * j;  // distToEnd > 2j  <=>  tp < tested_end
   int tp = 2 * j + 1, last_junc_pos = 0;
   bool have_last = false, have_fb = false, have_lf = false;
-  int last_tp = 0, last_fwd_idx = 0, rev_pos = 0, for_pos = 0;
-  long long last_slot = -1;
+  int last_tp = 0, last_fwd_idx = 0, rev_pos = 0, for_pos = 0, last_slot = -1;
   uint64_t fb_ext = 0, lf_ext = 0, v_prev1 = 0, v_prev2 = 0;  // v[n-1], v[n-2] of this sub-read's result list
   uint32_t n_out = 0;
   const bool pairs = !a.no_cleaning && a.spf != nullptr;
   const bool want_ext = a.ext != nullptr;
 
   auto push_out = [&](uint64_t real_ext) {
-    if (pairs && n_out >= 2 && lane == 0) spf_add_pair(a, v_prev2, real_ext);  // (v[i], v[i+2]) once the list has > 2 entries
-    // the first such pair is (v0, v2), issued when v2 arrives; a list that ends with exactly two
-    // entries is handled after the loop (:208-218)
+    // pairs (v[i], v[i+2]) once the list has more than two entries; a list that ends with exactly two
+    // entries is handled after the loop (:208-225)
+    if (pairs && n_out >= 2 && lane == 0) spf_add_pair(a, v_prev2, real_ext);
     v_prev2 = v_prev1; v_prev1 = real_ext; n_out++;
     if (want_ext) {
-      if (lane == 0) c.stage[c.n_stage] = real_ext;
+      if (lane == 0) c.S->stage[c.n_stage] = real_ext;
       c.n_stage++;
       __syncwarp();
       if (c.n_stage == EXT_STAGE - 1) ext_flush(a, c, lane);
@@ -254,23 +349,26 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
   while (true) {
     // ---- find_next_junction (:61-86): 32 half-steps per warp iteration
     bool found = false;
-    uint64_t key = 0;
-    long long slot = -1;
+    int slot = -1;
     while (tp < tested_end) {
       const int t = tp + lane;
       const bool active = t < tested_end;
       bool known = false, spc = false, tst = false;
       uint32_t cnt = 0;
-      uint64_t kk = 0;
-      long long sl = -1;
+      int sl = -1;
       if (active) {
         const int pos = t >> 1, dir = t & 1;
-        uint64_t fwd = kmer_at(a.packed, s0 + pos, k);
-        kk = dir ? fwd : revcomp(fwd, k);
-        sl = tbl_find(a, kk);
+        uint32_t f;
+        if (FAST) {
+          sl = c.S->slot[2 * (rel + pos) + dir];
+          f = c.S->flag[rel + pos];
+        } else {
+          const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
+          sl = tbl_find(a, dir ? fwd : revcomp(fwd, k));
+          f = a.flags[s0 + pos];
+        }
         known = sl >= 0;
         spc = t - last_junc_pos >= 2 * a.spacer - 1;
-        uint32_t f = a.flags[s0 + pos];
         cnt = dir ? (f >> 3) & 3u : (f >> 5) & 3u;
         tst = dir ? (f & 2u) != 0 : (f & 4u) != 0;
       }
@@ -281,55 +379,58 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       // NbJCheckKmer (:46): every half-step that reached testForJunction, the hit one included
       uint32_t jc = (active && ((upto >> lane) & 1u) && !known && !spc) ? cnt : 0u;
       jc = __reduce_add_sync(0xffffffffu, jc);
-      if (lane == 0) c.st[SS_JCHECK] += jc;
+      if (lane == 0) c.S->st[SS_JCHECK] += jc;
       if (hb) {
-        if (lane == 0) c.st[SS_PROCESSED] += hit;
+        if (lane == 0) c.S->st[SS_PROCESSED] += hit;
         tp += hit;
-        key = __shfl_sync(0xffffffffu, kk, hit);
         slot = __shfl_sync(0xffffffffu, sl, hit);
         found = true;
         break;
       }
-      if (lane == 0) c.st[SS_PROCESSED] += __popc(am);
+      if (lane == 0) c.S->st[SS_PROCESSED] += __popc(am);
       tp += 32;
     }
     if (!found) break;
     // ---- the junction at half-step tp (:134-192)
     const int pos = tp >> 1, dir = tp & 1;
-    const int real = dir ? (int)code_at(a.packed, s0 + pos + k) : (int)nt_comp(code_at(a.packed, s0 + pos - 1));
+    const uint64_t fwd = FAST ? c.S->kmer[rel + pos] : kmer_at_t<false>(a.packed, s0 + pos, k);
+    const uint64_t key = dir ? fwd : revcomp(fwd, k);
+    const int real = dir ? (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base)
+                         : (int)nt_comp(code_at_t<FAST>(c.pk, s0 + pos - 1 - c.pk_base));
     const int fwd_idx = dir ? real : 4, back_idx = dir ? 4 : real;  // getExtensionIndex (utils/ReadKmer.cpp:95-100)
-    int dist = 0;
-    if (lane == 0) {
-      if (slot < 0) {
-        bool created;
+    const bool known = slot >= 0;
+    bool created = false;
+    if (!known) {
+      if (lane == 0) {
         slot = tbl_insert(a, key, &created);
         if (created) a.stamps[slot] = c.stamp++;
       }
-      RecImg r = rec_load(a, slot);
-      r.add_cov(real);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      created = __shfl_sync(0xffffffffu, (int)created, 0) != 0;
+      c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
+      if (FAST) line_publish(a, c, key, slot, lane);
+    }
+    const bool seen = line_visited(c, slot, lane);
+    if (lane == 0) {
+      rec_add_cov(a, slot, real);
       if (have_last) {  // directLinkJunctions (utils/JunctionMap.cpp:551-561)
         const int d = tp - last_tp;
-        if (last_slot == slot) {
-          r.update(last_fwd_idx, d); r.link(last_fwd_idx);
-        } else {
-          RecImg q = rec_load(a, last_slot);
-          q.update(last_fwd_idx, d); q.link(last_fwd_idx);
-          rec_store(a, last_slot, q);
-        }
-        r.update(back_idx, d); r.link(back_idx);
+        rec_update(a, last_slot, last_fwd_idx, d); rec_link(a, last_slot, last_fwd_idx);
+        rec_update(a, slot, back_idx, d); rec_link(a, slot, back_idx);
       } else {
-        r.update(back_idx, tp - 2 * j);
+        rec_update(a, slot, back_idx, tp - 2 * j);
       }
-      rec_store(a, slot, r);
-      dist = (int)r.get(fwd_idx);
-      if (dist < 1) dist = 1;
-      c.st[SS_PROCESSED] += 1;
-      c.st[SS_SKIPPED] += (unsigned long long)(dist - 1);
     }
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    dist = __shfl_sync(0xffffffffu, dist, 0);
-    c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
-    __syncwarp();
+    int dist;
+    if (created) dist = 0;  // a zeroed record; back_idx != fwd_idx, so nothing written above shows here
+    else if (FAST && known && !seen) dist = c.S->hop[2 * (rel + pos) + dir];
+    else {
+      dist = lane == 0 ? (int)rec_dist_now(a, slot, fwd_idx) : 0;
+      dist = __shfl_sync(0xffffffffu, dist, 0);
+    }
+    if (dist < 1) dist = 1;
+    if (lane == 0) { c.S->st[SS_PROCESSED] += 1; c.S->st[SS_SKIPPED] += (unsigned long long)(dist - 1); }
+    line_visit(c, slot, lane);
     const uint64_t real_ext = ext_fwd(key, (uint32_t)real, mask);
     if (!dir) { if (!have_fb) { have_fb = true; fb_ext = real_ext; rev_pos = pos; } }
     else { if (!have_lf) { have_lf = true; for_pos = pos; } lf_ext = real_ext; }
@@ -340,27 +441,27 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
   }
   if (!have_last) {  // add_fake_junction (:92-104): mid-read, facing forward
     const int pos = len / 2 - k / 2;
-    const uint64_t key = kmer_at(a.packed, s0 + pos, k);
-    const int real = (int)code_at(a.packed, s0 + pos + k);
+    const uint64_t key = FAST ? c.S->kmer[rel + pos] : kmer_at_t<false>(a.packed, s0 + pos, k);
+    const int real = (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base);
+    int slot = 0;
+    bool created = false;
     if (lane == 0) {
-      c.st[SS_NOJUNC]++;
-      bool created;
-      long long slot = tbl_insert(a, key, &created);
+      c.S->st[SS_NOJUNC]++;
+      slot = tbl_insert(a, key, &created);
       if (created) a.stamps[slot] = c.stamp++;
-      RecImg r = rec_load(a, slot);
-      r.add_cov(real);
+      rec_add_cov(a, slot, real);
       const int mtp = 2 * pos + 1;
-      r.update(4, mtp - 2 * j);
-      r.update(real, (2 * len - mtp - 2 * k + 1) - 2 * j);
-      rec_store(a, slot, r);
+      rec_update(a, slot, 4, mtp - 2 * j);
+      rec_update(a, slot, real, (2 * len - mtp - 2 * k + 1) - 2 * j);
     }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    created = __shfl_sync(0xffffffffu, (int)created, 0) != 0;
     c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
-    __syncwarp();
+    if (FAST && created) line_publish(a, c, key, slot, lane);
+    line_visit(c, slot, lane);
     push_out(ext_fwd(key, (uint32_t)real, mask));
   } else if (lane == 0) {  // :205
-    RecImg r = rec_load(a, last_slot);
-    r.update(last_fwd_idx, (2 * len - last_tp - 2 * k + 1) - 2 * j);
-    rec_store(a, last_slot, r);
+    rec_update(a, last_slot, last_fwd_idx, (2 * len - last_tp - 2 * k + 1) - 2 * j);
   }
   __syncwarp();
   if (pairs && n_out == 2 && lane == 0) {  // :208-218
@@ -370,11 +471,12 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
 }
 
 // highest position in [s, pos) whose plane bit equals `want`, or -1; uniform across the warp
-__device__ long long find_prev_bit(const uint32_t* __restrict__ plane, uint32_t s, uint32_t pos, bool want) {
+template <bool SH>
+__device__ long long find_prev_bit(const uint32_t* plane, uint32_t s, uint32_t pos, bool want) {
   if (pos <= s) return -1;
   const uint32_t p = pos - 1, ws = s >> 5;
   uint32_t w = p >> 5;
-  uint32_t word = __ldg(plane + w);
+  uint32_t word = ldw<SH>(plane + w);
   if (!want) word = ~word;
   if ((p & 31) != 31) word &= (2u << (p & 31)) - 1u;
   while (true) {
@@ -382,31 +484,33 @@ __device__ long long find_prev_bit(const uint32_t* __restrict__ plane, uint32_t 
     if (word) return ((long long)w << 5) + 31 - __clz(word);
     if (w == ws) return -1;
     w--;
-    word = __ldg(plane + w);
+    word = ldw<SH>(plane + w);
     if (!want) word = ~word;
   }
 }
 
 // scanInputRead (:260-282) + getValidReads (:233-257) for the sequence line [ls, le)
+template <bool FAST>
 __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t le, int lane) {
   const int k = a.k, j = a.j;
   uint32_t pos = le;
   while (pos > ls) {  // getUnambiguousReads hands the segments over LAST first (utils/Kmer.cpp:64-80)
-    long long hi = find_prev_bit(a.inval, ls, pos, false);
+    // (positions are taken relative to inv_base while searching the validity plane)
+    long long hi = find_prev_bit<FAST>(c.inv, ls - c.inv_base, pos - c.inv_base, false);
     if (hi < 0) break;
-    const uint32_t ee = (uint32_t)hi + 1;
-    long long lo = find_prev_bit(a.inval, ls, ee, true);
-    const uint32_t ss = lo < 0 ? ls : (uint32_t)lo + 1;
+    const uint32_t ee = (uint32_t)hi + 1 + c.inv_base;
+    long long lo = find_prev_bit<FAST>(c.inv, ls - c.inv_base, ee - c.inv_base, true);
+    const uint32_t ss = lo < 0 ? ls : (uint32_t)lo + 1 + c.inv_base;
     pos = ss;
     const int L = (int)(ee - ss);
     if (L < k || L < k + 2 * j + 1) continue;
-    if (lane == 0) c.st[SS_UNAMBIG]++;
+    if (lane == 0) c.S->st[SS_UNAMBIG]++;
     // getValidReads: maximal runs of >= k Bloom-positive k-mers; npos is a virtual negative position
     const int npos = L - k + 1;
     int run_start = -1;
     for (int base = 0; base <= npos; base += 32) {
       const int i = base + lane;
-      const bool v = i < npos && (a.flags[ss + i] & 1u);
+      const bool v = i < npos && ((FAST ? c.S->flag[ss - ls + i] : a.flags[ss + i]) & 1u);
       const uint32_t m = __ballot_sync(0xffffffffu, v);
       const int lanes = npos + 1 - base < 32 ? npos + 1 - base : 32;
       int bit = 0;
@@ -420,11 +524,10 @@ __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
           uint32_t x = (~m) >> bit;
           if (!x) break;
           bit += __ffs(x) - 1;
-          if (bit >= lanes) bit = lanes - 1;  // unreachable: bit `lanes-1` of the last chunk is clear
           const int run_len = base + bit - run_start;
           if (run_len >= k) {
-            scan_forward(a, c, ss + run_start, run_len + k - 1, lane);
-            if (lane == 0) c.st[SS_NOERR]++;
+            scan_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane);
+            if (lane == 0) c.S->st[SS_NOERR]++;
           }
           run_start = -1;
         }
@@ -433,18 +536,69 @@ __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(STITCH_THREADS) stitch_kernel(StitchArgs a) {
+// phase 1: everything the walk will want to know about the line, all loads in flight together
+__device__ void prefetch_line(const StitchArgs& a, WarpScratch* S, uint32_t ls, int n_pos, int lane) {
+  const int k = a.k;
+  constexpr int PF = 2;  // positions per lane per pass
+  for (int base = 0; base < n_pos; base += 32 * PF) {
+    uint64_t fwd[PF], rcv[PF];
+    unsigned long long kf[PF], kb[PF];
+    uint64_t hf[PF], hb[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      const int pos = base + 32 * i + lane;
+      if (pos < n_pos) fwd[i] = kmer_at_t<true>(S->pk, (ls & 15u) + pos, k);
+    }
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      const int pos = base + 32 * i + lane;
+      if (pos < n_pos) {
+        rcv[i] = revcomp(fwd[i], k);
+        hf[i] = mix64(fwd[i]) & (a.cap - 1); hb[i] = mix64(rcv[i]) & (a.cap - 1);
+        kf[i] = __ldcg(a.keys + hf[i]); kb[i] = __ldcg(a.keys + hb[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+      const int pos = base + 32 * i + lane;
+      if (pos < n_pos) {
+        int sf, sb;
+        if (fwd[i] == KEY_EMPTY) sf = tbl_find(a, fwd[i]);
+        else {
+          while (kf[i] != fwd[i] && kf[i] != KEY_EMPTY) { hf[i] = (hf[i] + 1) & (a.cap - 1); kf[i] = __ldcg(a.keys + hf[i]); }
+          sf = kf[i] == fwd[i] ? (int)hf[i] : -1;
+        }
+        if (rcv[i] == KEY_EMPTY) sb = tbl_find(a, rcv[i]);
+        else {
+          while (kb[i] != rcv[i] && kb[i] != KEY_EMPTY) { hb[i] = (hb[i] + 1) & (a.cap - 1); kb[i] = __ldcg(a.keys + hb[i]); }
+          sb = kb[i] == rcv[i] ? (int)hb[i] : -1;
+        }
+        S->kmer[pos] = fwd[i];
+        S->slot[2 * pos + 1] = sf;
+        S->slot[2 * pos] = sb;
+        // dist[fwdIdx]: facing forward fwdIdx = the read's next base, facing backward fwdIdx = 4
+        if (sf >= 0) S->hop[2 * pos + 1] = (uint8_t)__ldcg(rec_field(a, sf, REC_DIST + (int)code_at_t<true>(S->pk, (ls & 15u) + pos + k)));
+        if (sb >= 0) S->hop[2 * pos] = (uint8_t)__ldcg(rec_field(a, sb, REC_DIST + 4));
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(StitchArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ unsigned long long stage[STITCH_WARPS][EXT_STAGE];
+  extern __shared__ __align__(16) unsigned char stitch_smem[];
+  WarpScratch* S = reinterpret_cast<WarpScratch*>(stitch_smem) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * STITCH_THREADS + threadIdx.x) >> 5;
-  const uint32_t n_warps = (gridDim.x * STITCH_THREADS) >> 5;
   StitchState* st = a.st;
   uint32_t next = __ldcg(&st->next), W = __ldcg(&st->W), round = __ldcg(&st->round);
+  if (W > a.w_max) W = a.w_max;
   WarpCtx c;
-  for (int i = 0; i < SS_COUNT; i++) c.st[i] = 0;
-  c.stage = stage[threadIdx.x >> 5];
-  c.n_stage = 0; c.part = 0; c.rec = 0; c.stamp = 0;
+  if (lane < SS_COUNT) S->st[lane] = 0;
+  __syncwarp();
+  c.S = S; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0; c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0;
   uint32_t status = ST_DONE;
 
   while (true) {
@@ -452,87 +606,129 @@ __global__ void __launch_bounds__(STITCH_THREADS) stitch_kernel(StitchArgs a) {
     const uint32_t nd = __ldcg(&st->nd[cur]);
     const uint32_t room = a.n_recs - next;
     const uint32_t n_new = W > nd ? (W - nd < room ? W - nd : room) : 0u;
-    const uint32_t n_win = nd + n_new;
+    const uint32_t n_win = nd + n_new;  // <= w_max <= warps of the grid
     if (n_win == 0) break;
     // n_entries / ext_used only move in phase 2, so this snapshot is the same in every thread
     const unsigned long long entries0 = __ldcg(&st->n_entries), ext0 = __ldcg(&st->ext_used);
-    if (gw == 0 && lane == 0) { __stcg(&st->nd[nxt], 0u); __stcg(&st->need[nxt], 0ull); }
-    // ---- phase 1: reservations
-    unsigned long long need = 0;
-    for (uint32_t e = gw; e < n_win; e += n_warps) {
-      const uint32_t rec = e < nd ? __ldcg(a.deferred[cur] + e) : next + (e - nd);
-      const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
-      const uint32_t len = le > ls ? le - ls : 0u;
-      line_reservations<0>(a, ls, len, rec, lane);
-      need += 2ull * len + 2;
+    if (gw == 0 && lane == 0) __stcg(&st->nd[nxt], 0u);
+    // ---- phase 1: reservations + lookups of the warp's record
+    const unsigned long long t0 = gtime_ns();
+    const bool have = gw < n_win;
+    uint32_t rec = 0, ls = 0, len = 0;
+    int n_res = 0;
+    bool fast = false;
+    if (have) {
+      rec = gw < nd ? __ldcg(a.deferred[cur] + gw) : next + (gw - nd);
+      ls = __ldg(a.seq_start + rec);
+      const uint32_t le = __ldg(a.seq_end + rec);
+      len = le > ls ? le - ls : 0u;
+      const int n_pos = len >= (uint32_t)a.k ? (int)(len - a.k + 1) : 0;
+      fast = n_pos > 0 && n_pos <= POS_CAP;
+      if (fast) {
+        // one coalesced sweep fetches everything the line needs from the planes
+        if (lane < 24) S->pk[lane] = __ldg(a.packed + (ls >> 4) + lane);
+        if (lane < 12) S->inv[lane] = __ldg(a.inval + (ls >> 5) + lane);
+        for (int pos = lane; pos < n_pos; pos += 32) S->flag[pos] = a.flags[ls + pos];
+        __syncwarp();
+        const unsigned long long ta = gtime_ns();
+        line_reservations<0, true>(a, S->pk, ls & 15u, len, rec, lane, S->reskey, &n_res);
+        const unsigned long long tb = gtime_ns();
+        prefetch_line(a, S, ls, n_pos, lane);
+        if (gw == 0 && lane == 0) { c.S->st[SS_T_P1A] += ta - t0; c.S->st[SS_T_P1B] += tb - ta; c.S->st[SS_T_P1C] += gtime_ns() - tb; }
+      } else {
+        line_reservations<0, false>(a, a.packed, ls, len, rec, lane, S->reskey, &n_res);
+      }
+      if (lane == 0 && 2ull * len + 2 > __ldcg(&st->max_need)) atomicMax(&st->max_need, 2ull * len + 2);
     }
-    if (lane == 0 && need) atomicAdd(&st->need[cur], need);
+    const unsigned long long t1 = gtime_ns();
     grid.sync();
+    const unsigned long long t2 = gtime_ns();
     {
-      const unsigned long long bound = __ldcg(&st->need[cur]);
+      const unsigned long long bound = __ldcg(&st->max_need) * n_win;
       if (entries0 + bound > (a.cap / 4) * 3) { status = ST_GROW_TABLE; break; }
       if (a.ext && ext0 + 2 * bound + n_win > a.ext_cap) { status = ST_DRAIN_EXT; break; }
     }
     // ---- phase 2: execute or defer
-    for (uint32_t e = gw; e < n_win; e += n_warps) {
-      const uint32_t rec = e < nd ? __ldcg(a.deferred[cur] + e) : next + (e - nd);
-      const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
-      const uint32_t len = le > ls ? le - ls : 0u;
-      const bool mine = line_reservations<1>(a, ls, len, rec, lane);
-      line_reservations<2>(a, ls, len, rec, lane);
+    if (have) {
+      bool mine;
+      if (n_res <= RES_CAP) {
+        bool ok = true;
+        for (int i = lane; i < n_res; i += 32)
+          if (__ldcg(a.res + S->reskey[i]) != rec) ok = false;
+        mine = __all_sync(0xffffffffu, ok);
+        for (int i = lane; i < n_res; i += 32)
+          if (__ldcg(a.res + S->reskey[i]) == rec) __stcg(a.res + S->reskey[i], RES_FREE);
+      } else {
+        mine = line_reservations<1, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
+        line_reservations<2, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
+      }
+      if (gw == 0 && lane == 0) c.S->st[SS_T_P2A] += gtime_ns() - t2;
       if (mine) {
-        c.rec = rec; c.part = 0; c.n_stage = 0;
+        c.rec = rec; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls;
         c.stamp = (a.rec_base + rec) << 20;
-        if (len) scan_line(a, c, ls, ls + len, lane);
+        if (fast) {
+          c.n_pos = (int)(len - a.k + 1);
+          c.pk = S->pk; c.pk_base = ls & ~15u; c.inv = S->inv; c.inv_base = ls & ~31u;
+          scan_line<true>(a, c, ls, ls + len, lane);
+        } else if (len) {
+          c.n_pos = 0;
+          c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0;
+          scan_line<false>(a, c, ls, ls + len, lane);
+        }
         if (a.ext && c.n_stage) ext_flush(a, c, lane);
       } else if (lane == 0) {
         a.deferred[nxt][atomicAdd(&st->nd[nxt], 1u)] = rec;
-        c.st[SS_DEFERRED]++;
+        c.S->st[SS_DEFERRED]++;
       }
     }
+    const unsigned long long t3 = gtime_ns();
     grid.sync();
+    if (gw == 0 && lane == 0) {
+      c.S->st[SS_T_PHASE1] += t1 - t0; c.S->st[SS_T_SYNC1] += t2 - t1; c.S->st[SS_T_PHASE2] += t3 - t2; c.S->st[SS_T_SYNC2] += gtime_ns() - t3;
+    }
     const uint32_t nd_next = __ldcg(&st->nd[nxt]);
-    if (nd_next * 4 > n_win) W = W / 2 > a.w_min ? W / 2 : a.w_min;
-    else if (nd_next * 10 < n_win && n_win >= W) W = W * 2 < a.w_max ? W * 2 : a.w_max;
+    if (nd_next * a.shrink_den > n_win) W = W / 2 > a.w_min ? W / 2 : a.w_min;
+    else if (nd_next * a.grow_den < n_win && n_win >= W) W = W * 2 < a.w_max ? W * 2 : a.w_max;
     next += n_new;
     round++;
-    if (gw == 0 && lane == 0) c.st[SS_ROUNDS]++;
+    if (gw == 0 && lane == 0) c.S->st[SS_ROUNDS]++;
   }
-  if (lane == 0)
-    for (int i = 0; i < SS_COUNT; i++)
-      if (c.st[i]) atomicAdd(&st->stats[i], c.st[i]);
+  __syncwarp();
+  if (lane < SS_COUNT && S->st[lane]) atomicAdd(&st->stats[lane], S->st[lane]);
   if (gw == 0 && lane == 0) {
     __stcg(&st->next, next); __stcg(&st->W, W); __stcg(&st->round, round); __stcg(&st->status, status);
   }
 }
 
 // ---- table maintenance ---------------------------------------------------------------------------
-__global__ void stitch_rehash_kernel(const unsigned long long* __restrict__ okeys, const uint4* __restrict__ orecs,
+__global__ void stitch_rehash_kernel(const unsigned long long* __restrict__ okeys, const uint32_t* __restrict__ orecs,
                                      const unsigned long long* __restrict__ ostamps, unsigned long long ocap,
-                                     unsigned long long* keys, uint4* recs, unsigned long long* stamps,
+                                     unsigned long long* keys, uint32_t* recs, unsigned long long* stamps,
                                      unsigned long long cap) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= ocap;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     unsigned long long key = okeys[i];
+    unsigned long long h;
     if (i == ocap) {  // the home of the KEY_EMPTY k-mer moves to the new last slot
-      keys[cap] = key; recs[cap] = orecs[i]; stamps[cap] = ostamps[i];
-      continue;
+      h = cap;
+      keys[cap] = key;
+    } else {
+      if (key == KEY_EMPTY) continue;
+      h = mix64(key) & (cap - 1);
+      while (atomicCAS(keys + h, KEY_EMPTY, key) != KEY_EMPTY) h = (h + 1) & (cap - 1);
     }
-    if (key == KEY_EMPTY) continue;
-    unsigned long long h = mix64(key) & (cap - 1);
-    while (atomicCAS(keys + h, KEY_EMPTY, key) != KEY_EMPTY) h = (h + 1) & (cap - 1);
-    recs[h] = orecs[i];
+    for (int f = 0; f < REC_WORDS; f++) recs[h * REC_WORDS + f] = orecs[i * REC_WORDS + f];
     stamps[h] = ostamps[i];
   }
 }
 
 struct JunctionOut {  // == faucet_junction_rec (include/faucet_gpu.h)
   unsigned long long kmer;
-  uint32_t body[4];   // dist[5] cov[4] linked[5] pad[2]
+  uint8_t dist[5], cov[4], linked[5], pad[2];
   unsigned long long stamp;
 };
 
-__global__ void stitch_collect_kernel(const unsigned long long* __restrict__ keys, const uint4* __restrict__ recs,
+__global__ void stitch_collect_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ recs,
                                       const unsigned long long* __restrict__ stamps, unsigned long long cap,
                                       unsigned int special, JunctionOut* __restrict__ out,
                                       unsigned long long* __restrict__ n_out) {
@@ -549,9 +745,13 @@ __global__ void stitch_collect_kernel(const unsigned long long* __restrict__ key
     if (lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(m));
     base = __shfl_sync(m, base, leader);
     unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
-    uint4 r = recs[i];
+    const uint32_t* r = recs + i * REC_WORDS;
     JunctionOut jo;
-    jo.kmer = key; jo.body[0] = r.x; jo.body[1] = r.y; jo.body[2] = r.z; jo.body[3] = r.w & 0xffffu; jo.stamp = stamps[i];
+    jo.kmer = key;
+    for (int f = 0; f < 5; f++) { jo.dist[f] = (uint8_t)r[REC_DIST + f]; jo.linked[f] = (r[REC_LINK] >> f) & 1u; }
+    for (int f = 0; f < 4; f++) jo.cov[f] = (uint8_t)(r[REC_COV + f] > 255u ? 255u : r[REC_COV + f]);
+    jo.pad[0] = jo.pad[1] = 0;
+    jo.stamp = stamps[i];
     out[o] = jo;
   }
 }

@@ -53,6 +53,8 @@ typedef struct {
   float h2d_ms, parse_ms, load_ms, scan_ms, stitch_ms, d2h_ms, total_ms;
   uint64_t kernel_launches;
   uint64_t stitch_rounds, stitch_deferred; /* reservation rounds / deferred records of the last scan */
+  uint64_t stitch_phase_ns[8];             /* ns in phase 1, barrier 1, phase 2, barrier 2, then phase-1 line fetch /
+                                              reservations / lookups and phase-2 check (warp 0 of the grid) */
 } faucet_timings;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
