@@ -88,6 +88,7 @@ def _load():
     L.faucet_session_stitch_batch.argtypes = [vp]
     L.faucet_session_get_bloom.argtypes = [vp, _u8p, _u8p]
     L.faucet_session_set_bloom.argtypes = [vp, _u8p]
+    L.faucet_session_read_bloom.argtypes = [vp, _u8p]
     L.faucet_session_get_junctions.argtypes = [vp, _recpp, _u64p, C.POINTER(ScanStats)]
     L.faucet_session_sync.argtypes = [vp]
     L.faucet_session_stream.argtypes = [vp]
@@ -99,6 +100,14 @@ def _load():
     L.faucet_session_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _u64p]
     L.faucet_session_set_profiling.argtypes = [vp, C.c_int]
     L.faucet_session_load_stats.argtypes = [vp, C.POINTER(LoadStats), C.c_uint64]
+    for f in (L.faucet_session_prepare_multi, L.faucet_session_close_peers, L.faucet_session_bloo1_local,
+              L.faucet_session_prefix_or, L.faucet_session_or_allreduce):
+        f.argtypes = [vp]
+    L.faucet_session_export.argtypes = [vp, C.c_int, C.c_void_p]
+    L.faucet_session_open_peers.argtypes = [vp, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.faucet_session_import_planes.argtypes = [vp, C.c_int, C.c_size_t, C.c_uint32, C.c_int]
+    L.faucet_session_batch_info.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+    L.faucet_host_plan_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, _u64p]
     return L
 
 
@@ -134,6 +143,14 @@ def timings():
     t = Timings()
     _check(lib.faucet_gpu_get_timings(C.byref(t)))
     return {n: (list(getattr(t, n)) if n == "stitch_phase_ns" else getattr(t, n)) for n, _ in t._fields_}
+
+
+def plan_shards(text, fastq, n_shards):
+    """record-aligned, byte-balanced contiguous ranges [(start, end)] of a FASTA/FASTQ text"""
+    addr, n, keep = _as_buffer(text)
+    offs = (C.c_uint64 * (n_shards + 1))()
+    _check(lib.faucet_host_plan_shards(addr, n, int(fastq), n_shards, offs))
+    return [(int(offs[i]), int(offs[i + 1])) for i in range(n_shards)]
 
 
 def geometry_from_reads(estimated_kmers, singletons, fp=0.04):
@@ -264,6 +281,13 @@ class Session:
         _check(lib.faucet_session_get_bloom(self.h, _ptr(b2), _ptr(b1)))
         return b2, b1
 
+    def get_bloom_full(self):
+        """the plain bloo2 array as it stands on the device (after an OR all-reduce: the merged filter)"""
+        nb = (1 << self.log2_tai) // 8
+        b2 = np.empty(nb, np.uint8)
+        _check(lib.faucet_session_read_bloom(self.h, _ptr(b2)))
+        return b2, None
+
     def set_bloom(self, bloo2):
         _check(lib.faucet_session_set_bloom(self.h, _ptr(bloo2)))
 
@@ -279,6 +303,49 @@ class Session:
 
     def sync(self):
         _check(lib.faucet_session_sync(self.h))
+
+    # ---- multi-GPU stage API (include/faucet_gpu.h, "multi-GPU") ----
+    BUFFERS = {"inval": 0, "packed": 1, "flags": 2, "seq_start": 3, "seq_end": 4, "bloo1_local": 5, "bloom": 6}
+
+    def prepare_multi(self):
+        _check(lib.faucet_session_prepare_multi(self.h))
+
+    def export(self, what):
+        buf = C.create_string_buffer(64)
+        _check(lib.faucet_session_export(self.h, self.BUFFERS[what], buf))
+        return buf.raw
+
+    def open_peers(self, what, handles, n_ranks, my_rank):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * n_ranks
+        _check(lib.faucet_session_open_peers(self.h, self.BUFFERS[what], blob, n_ranks, my_rank))
+
+    def close_peers(self):
+        _check(lib.faucet_session_close_peers(self.h))
+
+    def bloo1_local(self):
+        _check(lib.faucet_session_bloo1_local(self.h))
+
+    def prefix_or(self):
+        _check(lib.faucet_session_prefix_or(self.h))
+
+    def or_allreduce(self):
+        _check(lib.faucet_session_or_allreduce(self.h))
+
+    def import_planes(self, peer_rank, n_text, n_recs, fastq):
+        _check(lib.faucet_session_import_planes(self.h, peer_rank, n_text, n_recs, int(fastq)))
+
+    def batch_info(self):
+        n, r = C.c_size_t(), C.c_uint32()
+        _check(lib.faucet_session_batch_info(self.h, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def stitch_begin(self, paired_ends, no_cleaning, spf=None, spf_geom=(0, 0), lpf=None, lpf_geom=(0, 0)):
+        _check(lib.faucet_session_stitch_begin(self.h, int(paired_ends), int(no_cleaning), _ptr(spf), spf_geom[0],
+                                               spf_geom[1], _ptr(lpf), lpf_geom[0], lpf_geom[1]))
+
+    def stitch_batch(self):
+        _check(lib.faucet_session_stitch_batch(self.h))
 
     @property
     def stream(self):

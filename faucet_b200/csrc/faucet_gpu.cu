@@ -11,6 +11,7 @@
 #include "../../include/faucet_gpu.h"
 #include "kmer.cuh"
 #include "load.cuh"
+#include "multi.cuh"
 #include "parse.cuh"
 #include "scan.cuh"
 #include "pair_filter_host.hpp"
@@ -105,6 +106,11 @@ struct faucet_session {
   std::vector<faucet_junction_rec> recs_out;
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
+  // multi-GPU: peer buffers mapped through CUDA IPC (multi.cuh)
+  uint32_t* d_b1local = nullptr;            // OR of every k-mer of this GPU's shard (plain layout)
+  int n_ranks = 1, rank = 0;
+  void* peer[FAUCET_BUF_COUNT][MAX_PEERS] = {};
+  bool peers_open = false;
   const void* stitch_fn = nullptr;
   // bookkeeping
   uint64_t launches = 0;
@@ -319,6 +325,8 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
   cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
+  faucet_session_close_peers(s);
+  cudaFree(s->d_b1local);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -502,6 +510,13 @@ int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* blo
   if (bloo1_out) CU(cudaMemcpyAsync(bloo1_out, s->d_bloom1, s->tai() / 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return check_launch("bloom_split");
+}
+
+int faucet_session_read_bloom(faucet_session* s, uint8_t* bloo2_out) {
+  if (!s->d_bloom) return fail(FAUCET_E_STATE, "no bloo2 on the device");
+  CU(cudaMemcpyAsync(bloo2_out, s->d_bloom, s->tai() / 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
 }
 
 int faucet_session_set_bloom(faucet_session* s, const uint8_t* bloo2) {
@@ -762,6 +777,138 @@ int faucet_session_get_junctions(faucet_session* s, faucet_junction_rec** recs_o
   }
   if (n_out) *n_out = r.size();
   if (stats) *stats = s->sstats;
+  return 0;
+}
+
+// ---- multi-GPU (multi.cuh) -------------------------------------------------------------------------
+
+static void* session_buffer(faucet_session* s, int what) {
+  switch (what) {
+    case FAUCET_BUF_INVAL: return s->d_inval;
+    case FAUCET_BUF_PACKED: return s->d_packed;
+    case FAUCET_BUF_FLAGS: return s->d_flags;
+    case FAUCET_BUF_SEQ_START: return s->d_seq_start;
+    case FAUCET_BUF_SEQ_END: return s->d_seq_end;
+    case FAUCET_BUF_BLOO1_LOCAL: return s->d_b1local;
+    case FAUCET_BUF_BLOOM: return s->d_bloom;
+    default: return nullptr;
+  }
+}
+
+int faucet_session_prepare_multi(faucet_session* s) {
+  int rc;
+  if ((rc = ensure_load_buffers(s)) || (rc = ensure_scan_buffers(s))) return rc;
+  if (!s->d_b1local && (rc = dmalloc(&s->d_b1local, s->tai() / 32))) return rc;
+  CU(cudaMemsetAsync(s->d_b1local, 0, s->tai() / 8, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int faucet_session_export(faucet_session* s, int what, void* handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == FAUCET_IPC_HANDLE_BYTES, "handle size");
+  void* p = session_buffer(s, what);
+  if (!p) return fail(FAUCET_E_STATE, "buffer not allocated yet (call faucet_session_prepare_multi first)");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle_out, &h, sizeof h);
+  return 0;
+}
+
+int faucet_session_open_peers(faucet_session* s, int what, const void* handles, int n_ranks, int my_rank) {
+  if (n_ranks < 1 || n_ranks > MAX_PEERS || my_rank < 0 || my_rank >= n_ranks) return fail(FAUCET_E_ARG, "bad rank layout");
+  if (what < 0 || what >= FAUCET_BUF_COUNT) return fail(FAUCET_E_ARG, "bad buffer id");
+  s->n_ranks = n_ranks; s->rank = my_rank;
+  for (int r = 0; r < n_ranks; r++) {
+    if (r == my_rank) { s->peer[what][r] = session_buffer(s, what); continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * FAUCET_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer[what][r] = p;
+  }
+  s->peers_open = true;
+  return 0;
+}
+
+int faucet_session_close_peers(faucet_session* s) {
+  if (!s->peers_open) return 0;
+  for (int w = 0; w < FAUCET_BUF_COUNT; w++)
+    for (int r = 0; r < s->n_ranks; r++) {
+      if (r != s->rank && s->peer[w][r]) cudaIpcCloseMemHandle(s->peer[w][r]);
+      s->peer[w][r] = nullptr;
+    }
+  s->peers_open = false;
+  return 0;
+}
+
+// step 1: OR every k-mer of the parsed batch into this GPU's shard-wide bit array
+int faucet_session_bloo1_local(faucet_session* s) {
+  if (!s->parsed) return fail(FAUCET_E_STATE, "bloo1_local before parse");
+  if (!s->d_b1local) return fail(FAUCET_E_STATE, "call faucet_session_prepare_multi first");
+  LoadArgs a{};
+  a.inval = s->d_inval; a.packed = s->d_packed; a.n_words = (uint32_t)((s->n + 31) / 32);
+  a.tai_mask = s->tai() - 1; a.k = s->k; a.n_hash = s->n_hash;
+  const int grid = g.sm_count * 8;
+  switch (s->n_hash) {
+    case 1: bloom_add_all_kernel<1><<<grid, LOAD_THREADS, 0, s->stream>>>(a, s->d_b1local); break;
+    case 2: bloom_add_all_kernel<2><<<grid, LOAD_THREADS, 0, s->stream>>>(a, s->d_b1local); break;
+    case 3: bloom_add_all_kernel<3><<<grid, LOAD_THREADS, 0, s->stream>>>(a, s->d_b1local); break;
+    case 4: bloom_add_all_kernel<4><<<grid, LOAD_THREADS, 0, s->stream>>>(a, s->d_b1local); break;
+    default: bloom_add_all_kernel<0><<<grid, LOAD_THREADS, 0, s->stream>>>(a, s->d_b1local); break;
+  }
+  s->launches++;
+  return check_launch("bloom_add_all");
+}
+
+// step 2: bloo1 := OR of the shard arrays of the GPUs before this one (bloo2 := empty, stamps fresh)
+int faucet_session_prefix_or(faucet_session* s) {
+  if (!s->peers_open) return fail(FAUCET_E_STATE, "peers not opened");
+  int rc = faucet_session_reset_filters(s);
+  if (rc) return rc;
+  PeerPtrs p{};
+  for (int r = 0; r < s->rank; r++) p.in[r] = (const uint32_t*)s->peer[FAUCET_BUF_BLOO1_LOCAL][r];
+  bloom_prefix_or_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(p, s->rank, s->d_fused, s->d_stamps, s->tai() / 32);
+  s->launches++;
+  return check_launch("bloom_prefix_or");
+}
+
+// step 4: in-place OR all-reduce of the per-shard bloo2 arrays (d_bloom of every GPU).  The caller
+// puts a cross-process barrier before (all shards loaded and split) and after (all ranges written).
+int faucet_session_or_allreduce(faucet_session* s) {
+  if (!s->peers_open) return fail(FAUCET_E_STATE, "peers not opened");
+  const uint64_t n_words = s->tai() / 32;
+  if (n_words % 4) return fail(FAUCET_E_ARG, "Bloom filter too small for the multi-GPU reduce");
+  PeerPtrs p{};
+  for (int r = 0; r < s->n_ranks; r++) p.out[r] = (uint32_t*)s->peer[FAUCET_BUF_BLOOM][r];
+  const uint64_t vecs = n_words / 4;
+  const uint64_t v0 = vecs * s->rank / s->n_ranks, v1 = vecs * (s->rank + 1) / s->n_ranks;
+  if (v1 > v0) {
+    const int grid = (int)std::min<uint64_t>(g.sm_count * 8, (v1 - v0 + 255) / 256);
+    bloom_or_allreduce_kernel<<<grid, 256, 0, s->stream>>>(p, s->n_ranks, v0 * 4, v1 * 4);
+    s->launches++;
+  }
+  return check_launch("bloom_or_allreduce");
+}
+
+// pass 2 on GPU 0: pull the parsed + flagged planes of `peer_rank` over NVLink into this session
+int faucet_session_import_planes(faucet_session* s, int peer_rank, size_t n_text, uint32_t n_recs, int fastq) {
+  if (!s->peers_open || peer_rank < 0 || peer_rank >= s->n_ranks) return fail(FAUCET_E_STATE, "peer not opened");
+  if (n_text > s->cap) return fail(FAUCET_E_ARG, "peer batch larger than this session's capacity");
+  if (peer_rank != s->rank) {
+    const size_t words = (n_text + 31) / 32 + 2;
+    CU(cudaMemcpyAsync(s->d_inval, s->peer[FAUCET_BUF_INVAL][peer_rank], words * 4, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_packed, s->peer[FAUCET_BUF_PACKED][peer_rank], (2 * words + 2) * 4, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_flags, s->peer[FAUCET_BUF_FLAGS][peer_rank], n_text, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_seq_start, s->peer[FAUCET_BUF_SEQ_START][peer_rank], (size_t)n_recs * 4, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_seq_end, s->peer[FAUCET_BUF_SEQ_END][peer_rank], (size_t)n_recs * 4, cudaMemcpyDeviceToDevice, s->stream));
+  }
+  s->n = n_text; s->n_recs = n_recs; s->fastq = fastq != 0; s->parsed = true;
+  return 0;
+}
+
+int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_recs) {
+  if (!s->parsed) return fail(FAUCET_E_STATE, "no parsed batch");
+  *n_text = s->n; *n_recs = s->n_recs;
   return 0;
 }
 

@@ -90,3 +90,27 @@ extern "C" int faucet_geometry_from_reads(uint64_t estimated_kmers, uint64_t sin
   if (!ok || !(p1 > 0)) return FAUCET_E_ARG;
   return faucet_geometry_optimal(estimated_kmers, (float)p1, log2_tai_out, n_hash_out);
 }
+
+// ---- shard planning for the multi-GPU path (host only) ---------------------------------------------
+// Cuts a FASTA/FASTQ text into n_shards contiguous ranges that start on record boundaries (a record =
+// 2 or 4 lines, as the reference's getline loops see it: utils/Bloom.cpp:280-282,340) and are balanced
+// by bytes.  offsets_out receives n_shards + 1 offsets, offsets_out[0] = 0, offsets_out[n_shards] = n.
+#include <cstring>
+extern "C" int faucet_host_plan_shards(const char* text, size_t n, int fastq, int n_shards, uint64_t* offsets_out) {
+  if (n_shards < 1 || !offsets_out) return FAUCET_E_ARG;
+  const uint64_t period = fastq ? 4 : 2;
+  offsets_out[0] = 0;
+  int next = 1;
+  uint64_t lines = 0;
+  size_t pos = 0;
+  while (next < n_shards && pos < n) {
+    const char* nl = (const char*)memchr(text + pos, '\n', n - pos);
+    if (!nl) break;
+    pos = (size_t)(nl - text) + 1;
+    lines++;
+    if (lines % period == 0)
+      while (next < n_shards && pos >= (uint64_t)n * next / n_shards) offsets_out[next++] = pos;
+  }
+  while (next <= n_shards) offsets_out[next++] = n;
+  return 0;
+}

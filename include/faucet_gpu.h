@@ -138,6 +138,7 @@ int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_
 int faucet_session_set_profiling(faucet_session* s, int on);   /* per-kernel CUDA-event timing */
 int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* bloo1_out);
 int faucet_session_set_bloom(faucet_session* s, const uint8_t* bloo2);
+int faucet_session_read_bloom(faucet_session* s, uint8_t* bloo2_out); /* device bloo2 as it stands (e.g. after the OR all-reduce) */
 int faucet_session_get_junctions(faucet_session* s, faucet_junction_rec** recs_out, uint64_t* n_out,
                                  faucet_scan_stats* stats);
 int faucet_session_sync(faucet_session* s);
@@ -149,6 +150,30 @@ uint64_t faucet_session_kernel_launches(faucet_session* s);
 /* event-timed duration (ms) accumulated per named kernel since the last reset:
  * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch */
 int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64_t* launches_out);
+
+/* ---- multi-GPU: one process per GPU of one NVSwitch box, peer HBM mapped through CUDA IPC -----
+ * (DESIGN.md section 6).  Exact sharded pass 1: shard g = g-th contiguous range of the stream.
+ *   prepare_multi; parse; bloo1_local            (every rank, over its shard)
+ *   export/open_peers(FAUCET_BUF_BLOO1_LOCAL, FAUCET_BUF_BLOOM, planes...)   handles exchanged by the caller
+ *   [barrier] prefix_or; load; get_bloom(NULL,NULL) [barrier] or_allreduce [barrier]
+ * Pass 2: scan_flags on every rank; rank 0 stitches its own shard, then import_planes(r) + stitch_batch
+ * for r = 1..N-1 (the junction map lives on rank 0). */
+enum { FAUCET_BUF_INVAL = 0, FAUCET_BUF_PACKED, FAUCET_BUF_FLAGS, FAUCET_BUF_SEQ_START, FAUCET_BUF_SEQ_END,
+       FAUCET_BUF_BLOO1_LOCAL, FAUCET_BUF_BLOOM, FAUCET_BUF_COUNT };
+#define FAUCET_IPC_HANDLE_BYTES 64
+int faucet_session_prepare_multi(faucet_session* s);   /* allocates every exportable buffer */
+int faucet_session_export(faucet_session* s, int what, void* handle_out /* 64 bytes */);
+int faucet_session_open_peers(faucet_session* s, int what, const void* handles /* n_ranks x 64 bytes */,
+                              int n_ranks, int my_rank);
+int faucet_session_close_peers(faucet_session* s);
+int faucet_session_bloo1_local(faucet_session* s);
+int faucet_session_prefix_or(faucet_session* s);
+int faucet_session_or_allreduce(faucet_session* s);
+int faucet_session_import_planes(faucet_session* s, int peer_rank, size_t n_text, uint32_t n_recs, int fastq);
+int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_recs);
+/* host helper: n_shards contiguous, record-aligned, byte-balanced ranges of a FASTA/FASTQ text;
+ * offsets_out has n_shards + 1 entries */
+int faucet_host_plan_shards(const char* text, size_t n, int fastq, int n_shards, uint64_t* offsets_out);
 
 #ifdef __cplusplus
 }
