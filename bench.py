@@ -33,13 +33,14 @@ WORKLOADS = {
 J, MAX_SPACER, FP = 1, 100, 0.04  # faucet defaults: -j 1, -max_spacer_dist 100, -fp 0.04 (src/Faucet.h:14-48)
 
 
-def gen_dataset(w, seed, pairs=None, tag=""):
+def gen_dataset(w, seed, pairs=None, tag="", stream=0):
+    """stream > 0: another read sample of the SAME genome (the shard of rank `stream` in a multi-GPU job)"""
     from _oracle import gen_reads
     d = os.environ.get("FAUCET_BENCH_TMP", "/tmp/faucet_bench")
     os.makedirs(d, exist_ok=True)
-    path = os.path.join(d, f"{w['genome']}_{w['cov']}_{w['length']}_{seed}{tag}.fq")
+    path = os.path.join(d, f"{w['genome']}_{w['cov']}_{w['length']}_{seed}_{stream}{tag}.fq")
     if not os.path.exists(path):
-        kw = dict(genome=w["genome"], cov=w["cov"], length=w["length"], insert=w["insert"], seed=seed)
+        kw = dict(genome=w["genome"], cov=w["cov"], length=w["length"], insert=w["insert"], seed=seed, stream=stream)
         if pairs:
             kw["pairs"] = pairs
         gen_reads(path + ".tmp", **kw)
@@ -177,8 +178,9 @@ def run_ours(args, w):
 
     k = w["k"]
     _, lt, nh = fb.geometry_from_reads(w["est"], w["sing"], FP)
-    # weak scaling: every rank streams its own read set of the named shape (different seed per rank)
-    path = gen_dataset(w, seed=1 + rank)
+    # weak scaling: rank g holds shard g of ONE job = N read samples (100x each) of the same genome,
+    # concatenated in rank order; the sharded job is exact (same result as the reference on that file)
+    path = gen_dataset(w, seed=1, stream=rank)
     raw = np.fromfile(path, dtype=np.uint8)
     n_text = raw.size
     reads = int(np.count_nonzero(raw == 10)) // 4
@@ -187,17 +189,32 @@ def run_ours(args, w):
     host.numpy()[:] = raw
     del raw
     dev = host.cuda()
+    cap = torch.tensor([n_text], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
 
-    sess = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=n_text)
+    sess = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=int(cap.item()) + 4096)
+    job = None
+    if world > 1:
+        from faucet_b200.multi import ShardedJob, TorchComm
+        job = ShardedJob(sess, TorchComm(torch.device("cuda", local)))
+        job.setup()
+
+    def step_from(src, device):
+        sess.set_text(src, device=device)
+        if job is None:
+            sess.reset_filters()
+            sess.parse(True)
+            sess.load()
+            sess.get_bloom(to_host=False)
+            sess.scan_flags()
+            return sess.stitch(True, True)
+        job.load(True)
+        job.scan(True, True, True)
+        return 0
 
     def step_resident():
-        sess.set_text((dev.data_ptr(), n_text), device=True)  # D2D: the batch is already in HBM
-        sess.reset_filters()
-        sess.parse(True)
-        sess.load()
-        sess.get_bloom(to_host=False)
-        sess.scan_flags()
-        return sess.stitch(True, True)
+        return step_from((dev.data_ptr(), n_text), True)  # D2D: the batch is already in HBM
 
     def barrier():
         torch.cuda.synchronize()
@@ -221,32 +238,43 @@ def run_ours(args, w):
     clk = clocks.stop()
     launches = sess.launches - launches0
     kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch")}
-    sess.junctions()  # gathers the map once (not timed) so that the stitch round counters are published
-    stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith("stitch_")}
     sess.set_profiling(False)
     lstats = sess.load_stats()
-    b2, _ = sess.get_bloom()
+    stitch_info, n_junc = {}, 0
+    if rank == 0:
+        recs, _ = sess.junctions()  # gathers the map once (not timed); publishes the stitch round counters
+        n_junc = len(recs)
+        stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith("stitch_")}
+    b2, _ = sess.get_bloom_full() if world > 1 else sess.get_bloom()
     weight2 = float(np.unpackbits(b2).sum()) / (1 << lt)
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + D2H inside the timed region
     hptr = (host.data_ptr(), n_text)
     bloo2 = np.empty((1 << lt) // 8, np.uint8)
-
-    def step_e2e():
-        fb.load_two_filters_mem(hptr, True, k, lt, nh, out=bloo2)
-        recs, st = fb.scan_mem(hptr, True, True, True, k, J, MAX_SPACER, bloo2, lt, nh)
-        return len(recs)
-
-    sess.close()
     e2e_steps = max(1, min(args.steps, 3))
+    if world == 1:
+        def step_e2e():
+            fb.load_two_filters_mem(hptr, True, k, lt, nh, out=bloo2)
+            recs, st = fb.scan_mem(hptr, True, True, True, k, J, MAX_SPACER, bloo2, lt, nh)
+            return len(recs)
+        sess.close()
+    else:
+        def step_e2e():  # the sharded job fed from pinned host memory; results read back to the host
+            step_from(hptr, False)
+            sess.get_bloom_full()
+            return len(sess.junctions()[0]) if rank == 0 else 0
     step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         n_junc_e2e = step_e2e()
-    torch.cuda.synchronize()
+    barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    assert n_junc_e2e == n_junc
+    assert n_junc_e2e == n_junc, (n_junc_e2e, n_junc)
+    if job is not None:
+        barrier()
+        sess.close_peers()
+        sess.close()
 
     # max over ranks, whole-job aggregate
     t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
@@ -274,9 +302,10 @@ def run_ours(args, w):
                        "max_spacer_dist": MAX_SPACER, "reads_per_gpu": reads, "kmers_per_pass_per_gpu": kmers_per_pass,
                        "text_bytes_per_gpu": n_text, "junctions": int(n_junc),
                        "l2": "inputs (%.0f MB text + planes) exceed the 126 MB L2" % (n_text / 1e6),
-                       "parallelism": "replicated read sets, one per GPU" if world > 1 else "single GPU"},
+                       "parallelism": ("%d contiguous shards of one read stream (one per GPU): exact P2P prefix-OR / OR all-reduce "
+                                       "of the Bloom filters over NVLink, junction stitch on GPU 0" % world) if world > 1 else "single GPU"},
             "e2e": {"value": kmers_all / (e2e_ms_all * 1e-3), "unit": "k-mers/s",
-                    "h2d_bytes_per_step": 2 * n_text + bloo2.nbytes,
+                    "h2d_bytes_per_step": (2 * n_text + bloo2.nbytes) if world == 1 else n_text,
                     "d2h_bytes_per_step": bloo2.nbytes + 32 * int(n_junc), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clk,

@@ -243,7 +243,7 @@ def gen_reads(path, **kw):
     if not os.path.exists(exe) or os.path.getmtime(src) > os.path.getmtime(exe):
         subprocess.check_call(["gcc", "-O2", "-o", exe, src])
     flags = {"genome": "-g", "cov": "-c", "length": "-l", "insert": "-i", "seed": "-s", "err": "-e",
-             "nrate": "-n", "pairs": "-p"}
+             "nrate": "-n", "pairs": "-p", "stream": "-S"}
     cmd = [exe, "-o", path]
     for k, v in kw.items():
         if k in flags:

@@ -5,7 +5,7 @@
  * mate 2 = reverse complement of the fragment's far end, interleaved 4-line FASTQ (or 2-line FASTA)
  * with constant quality, optional i.i.d. substitution errors and optional 'N' bases.
  *
- *   gen_reads -o out.fq -g 1000000 -c 30 -l 100 -i 300 -s 1 [-e 0.005] [-r] [-n 0.001] [-a] [-p N]
+ *   gen_reads -o out.fq -g 1000000 -c 30 -l 100 -i 300 -s 1 [-e 0.005] [-r] [-n 0.001] [-a] [-p N] [-S stream]
  *
  * Uses its own splitmix64/xoshiro256** so the byte stream is identical on every platform.
  */
@@ -38,7 +38,7 @@ static inline char comp(char c) {
 
 int main(int argc, char** argv) {
   const char* out = NULL;
-  uint64_t G = 1000000, seed = 1, max_pairs = 0;
+  uint64_t G = 1000000, seed = 1, max_pairs = 0, stream = 0;
   double cov = 30, err = 0, nrate = 0;
   int L = 100, insert = 300, repeats = 0, fasta = 0, lower = 0;
   for (int i = 1; i < argc; i++) {
@@ -54,6 +54,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-a")) fasta = 1;                 /* 2-line FASTA instead of FASTQ */
     else if (!strcmp(argv[i], "-w")) lower = 1;                 /* sprinkle lowercase bases (rate = nrate) */
     else if (!strcmp(argv[i], "-p")) max_pairs = strtoull(argv[++i], 0, 10);
+    else if (!strcmp(argv[i], "-S")) stream = strtoull(argv[++i], 0, 10);  /* same genome, another read sample */
     else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
   }
   if (!out || insert < L || G < (uint64_t)insert) { fprintf(stderr, "usage: gen_reads -o FILE [-g G -c COV -l L -i INSERT -s SEED -e ERR -n NRATE -r -a -p PAIRS]\n"); return 2; }
@@ -69,6 +70,7 @@ int main(int argc, char** argv) {
       for (int c = 0; c < 5; c++) memcpy(g + below(G - 400), unit, 400);
     }
   }
+  if (stream) seed_rng(seed ^ (0x9e3779b97f4a7c15ULL * stream));  /* the genome above depends on -s only */
   uint64_t pairs = (uint64_t)(G * cov / (2.0 * L));
   if (max_pairs && pairs > max_pairs) pairs = max_pairs;
   FILE* f = fopen(out, "wb");
