@@ -96,6 +96,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("bytes")
+    except (OSError, ValueError):
+        return None
+
+
 def algorithmic_bytes(w, n_hash, weight2, r_contained):
     """SURVEY.md section 8(d) sector model, bytes per k-mer"""
     rho = w["length"] / (w["length"] - w["k"] + 1)
@@ -253,9 +262,15 @@ def run_ours(args, w):
     bloo2 = np.empty((1 << lt) // 8, np.uint8)
     e2e_steps = max(1, min(args.steps, 3))
     if world == 1:
+        e2e_parts = [0.0, 0.0]
+
         def step_e2e():
+            ta = time.perf_counter()
             fb.load_two_filters_mem(hptr, True, k, lt, nh, out=bloo2)
+            tb = time.perf_counter()
             recs, st = fb.scan_mem(hptr, True, True, True, k, J, MAX_SPACER, bloo2, lt, nh)
+            e2e_parts[0] += tb - ta
+            e2e_parts[1] += time.perf_counter() - tb
             return len(recs)
         sess.close()
     else:
@@ -264,6 +279,8 @@ def run_ours(args, w):
             sess.get_bloom_full()
             return len(sess.junctions()[0]) if rank == 0 else 0
     step_e2e()
+    if world == 1:
+        e2e_parts[0] = e2e_parts[1] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -306,11 +323,13 @@ def run_ours(args, w):
                                        "of the Bloom filters over NVLink, junction stitch on GPU 0" % world) if world > 1 else "single GPU"},
             "e2e": {"value": kmers_all / (e2e_ms_all * 1e-3), "unit": "k-mers/s",
                     "h2d_bytes_per_step": (2 * n_text + bloo2.nbytes) if world == 1 else n_text,
-                    "d2h_bytes_per_step": bloo2.nbytes + 32 * int(n_junc), "steps": e2e_steps},
+                    "d2h_bytes_per_step": bloo2.nbytes + 32 * int(n_junc), "steps": e2e_steps,
+                    **({"load_call_ms": 1e3 * e2e_parts[0] / e2e_steps, "scan_call_ms": 1e3 * e2e_parts[1] / e2e_steps}
+                       if world == 1 else {})},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_kind": peak_kind,
                          "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms},
             "kernels_ms_per_step": {n: v[0] / args.steps for n, v in kernel_ms.items()},
             "bloom_weight2": weight2, "contained_fraction": r_contained, "stitch": stitch_info,

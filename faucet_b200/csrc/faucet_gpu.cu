@@ -26,7 +26,7 @@ struct Global {
   int device = 0;
   int sm_count = 148;
   std::string err;
-  size_t batch_bytes = (size_t)128 << 20;  // text bytes per pipelined device batch of the whole-pass entry points
+  size_t batch_bytes = (size_t)256 << 20;  // text bytes per pipelined device batch of the whole-pass entry points
   uint64_t epoch_limit = 0xfffffffeull;
   unsigned long long table_cap0 = 1ull << 22;  // initial junction-table slots (grows by rehash)
   int res_log2 = 24;                           // reservation table entries (u32 each)
@@ -106,6 +106,10 @@ struct faucet_session {
   std::vector<faucet_junction_rec> recs_out;
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
+  uint32_t *d_hist = nullptr, *d_hist_sums = nullptr;  // junction-creation counts per record (ordering)
+  unsigned long long hist_cap = 0;
+  faucet_junction_rec* d_out = nullptr;
+  size_t out_cap = 0;
   // multi-GPU: peer buffers mapped through CUDA IPC (multi.cuh)
   uint32_t* d_b1local = nullptr;            // OR of every k-mer of this GPU's shard (plain layout)
   int n_ranks = 1, rank = 0;
@@ -326,7 +330,7 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   faucet_session_close_peers(s);
-  cudaFree(s->d_b1local);
+  cudaFree(s->d_b1local); cudaFree(s->d_hist); cudaFree(s->d_hist_sums); cudaFree(s->d_out);
   if (s->t0) cudaEventDestroy(s->t0);
   if (s->t1) cudaEventDestroy(s->t1);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -723,24 +727,36 @@ static int stitch_finish(faucet_session* s) {
   CU(cudaMemcpyAsync(&st, s->d_st, sizeof st, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   const size_t n = (size_t)st.n_entries;
-  JunctionOut* d_out = nullptr;
-  unsigned long long* d_n = nullptr;
   int rc;
-  if ((rc = dmalloc(&d_out, std::max<size_t>(1, n))) || (rc = dmalloc(&d_n, 1))) { cudaFree(d_out); return rc; }
-  CU(cudaMemsetAsync(d_n, 0, 8, s->stream));
-  stitch_collect_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(s->d_keys, s->d_recs, s->d_jstamps, s->tbl_cap, st.special, d_out, d_n);
-  s->launches++;
+  // creation order on the device: counting sort over record indices (stitch.cuh)
+  const unsigned long long n_hist = s->rec_base + 1;
+  const unsigned long long n_blocks = (n_hist + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  if (n_hist > s->hist_cap) {
+    cudaFree(s->d_hist); cudaFree(s->d_hist_sums); s->d_hist = nullptr; s->d_hist_sums = nullptr;
+    s->hist_cap = n_hist + n_hist / 4;
+    if ((rc = dmalloc(&s->d_hist, s->hist_cap)) || (rc = dmalloc(&s->d_hist_sums, s->hist_cap / SCAN_CHUNK + 2))) return rc;
+  }
+  if (n > s->out_cap) {
+    cudaFree(s->d_out); s->d_out = nullptr;
+    s->out_cap = n + n / 4 + 1024;
+    if ((rc = dmalloc(&s->d_out, s->out_cap))) return rc;
+  }
   static_assert(sizeof(JunctionOut) == sizeof(faucet_junction_rec), "record layouts must agree");
+  if (n) {
+    CU(cudaMemsetAsync(s->d_hist, 0, n_hist * 4, s->stream));
+    stitch_count_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(s->d_keys, s->d_jstamps, s->tbl_cap, st.special, s->d_hist);
+    scan_reduce_kernel<<<(unsigned)n_blocks, 256, 0, s->stream>>>(s->d_hist, n_hist, s->d_hist_sums);
+    scan_sums_kernel<<<1, 1024, 0, s->stream>>>(s->d_hist_sums, n_blocks);
+    scan_apply_kernel<<<(unsigned)n_blocks, 256, 0, s->stream>>>(s->d_hist, n_hist, s->d_hist_sums);
+    stitch_emit_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(s->d_keys, s->d_recs, s->d_jstamps, s->tbl_cap, st.special,
+                                                            s->d_hist, (JunctionOut*)s->d_out);
+    s->launches += 5;
+  }
   s->recs_out.resize(n);
-  if (n) CU(cudaMemcpyAsync(s->recs_out.data(), d_out, n * sizeof(JunctionOut), cudaMemcpyDeviceToHost, s->stream));
+  if (n) CU(cudaMemcpyAsync(s->recs_out.data(), s->d_out, n * sizeof(JunctionOut), cudaMemcpyDeviceToHost, s->stream));
   if (s->h_spf) CU(cudaMemcpyAsync(s->h_spf, s->d_spf, ((size_t)1 << s->spf_log2) / 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
-  cudaFree(d_out); cudaFree(d_n);
   if ((rc = check_launch("stitch_collect"))) return rc;
-  // creation order = (record index, n-th creation inside the record)
-  std::sort(s->recs_out.begin(), s->recs_out.end(),
-            [](const faucet_junction_rec& x, const faucet_junction_rec& y) { return x.creation_rank < y.creation_rank; });
-  for (size_t i = 0; i < n; i++) s->recs_out[i].creation_rank = i;
   faucet_scan_stats& o = s->sstats;
   o.n_junctions = n;
   o.nb_jcheck_kmer = st.stats[SS_JCHECK]; o.nb_no_juncs = st.stats[SS_NOJUNC]; o.nb_processed = st.stats[SS_PROCESSED];
@@ -941,7 +957,9 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
   *total_lines = 0;
   const size_t room = s->cap - TAIL_MAX;
   int buf = 0;
-  size_t len = std::min(room, n);
+  // batches ramp up from 32 MiB so that the first, un-overlapped H2D copy is short
+  size_t ramp = std::min(room, (size_t)32 << 20);
+  size_t len = std::min(ramp, n);
   int rc = stage_text(s, buf, text, len, cudaMemcpyHostToDevice, s->copy_stream);
   if (rc) return rc;
   CU(cudaEventRecord(s->ev_copied[buf], s->copy_stream));
@@ -957,7 +975,8 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
       uint64_t lines = s->h_pctr.total_newlines;
       *total_lines += lines - (lines % (fastq ? 4 : 2));
       // next batch -> the other buffer, while this one is being processed
-      const size_t noff = off + consumed, nlen = std::min(room, n - noff);
+      ramp = std::min(room, ramp * 2);
+      const size_t noff = off + consumed, nlen = std::min(ramp, n - noff);
       if ((rc = stage_text(s, buf ^ 1, text + noff, nlen, cudaMemcpyHostToDevice, s->copy_stream))) return rc;
       CU(cudaEventRecord(s->ev_copied[buf ^ 1], s->copy_stream));
     } else {
@@ -966,7 +985,7 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
     if ((rc = per_batch((const uint8_t*)text + off, (size_t)0, consumed, final_batch))) return rc;
     if (final_batch) break;
     off += consumed;
-    len = std::min(room, n - off);
+    len = std::min(ramp, n - off);
     buf ^= 1;
   }
   return 0;

@@ -725,34 +725,113 @@ __global__ void stitch_rehash_kernel(const unsigned long long* __restrict__ okey
 struct JunctionOut {  // == faucet_junction_rec (include/faucet_gpu.h)
   unsigned long long kmer;
   uint8_t dist[5], cov[4], linked[5], pad[2];
-  unsigned long long stamp;
+  unsigned long long rank;
 };
 
-__global__ void stitch_collect_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ recs,
-                                      const unsigned long long* __restrict__ stamps, unsigned long long cap,
-                                      unsigned int special, JunctionOut* __restrict__ out,
-                                      unsigned long long* __restrict__ n_out) {
+// Creation order without a sort: stamp = (record index << 20 | n-th creation of that record), and the
+// n-th creations of a record are dense, so  rank = (#junctions created by earlier records) + n.
+//   count:   hist[record]++ for every junction          scan: exclusive prefix sum of hist
+//   emit:    out[prefix[record] + n] = junction
+__global__ void stitch_count_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ stamps,
+                                    unsigned long long cap, unsigned int special, uint32_t* __restrict__ hist) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= cap;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    unsigned long long key = keys[i];
-    bool occ = i == cap ? special != 0 : key != KEY_EMPTY;
-    uint32_t m = __ballot_sync(__activemask(), occ);
+    const bool occ = i == cap ? special != 0 : keys[i] != KEY_EMPTY;
+    if (occ) atomicAdd(hist + (stamps[i] >> 20), 1u);
+  }
+}
+
+constexpr int SCAN_CHUNK = 4096;  // elements per CTA of the prefix sum (256 threads x 16)
+__global__ void __launch_bounds__(256) scan_reduce_kernel(const uint32_t* __restrict__ in, unsigned long long n,
+                                                          uint32_t* __restrict__ block_sums) {
+  const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_CHUNK;
+  uint32_t v = 0;
+  for (int i = threadIdx.x; i < SCAN_CHUNK; i += 256)
+    if (base + i < n) v += in[base + i];
+  __shared__ uint32_t ws[8];
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < 8; i++) t += ws[i];
+    block_sums[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ sums, unsigned long long n) {
+  __shared__ uint32_t wtot[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (unsigned long long base = 0; base < n; base += 1024) {
+    const unsigned long long i = base + threadIdx.x;
+    const uint32_t v = i < n ? sums[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t t = wtot[threadIdx.x];
+      uint32_t sx = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, sx, o);
+        if (threadIdx.x >= o) sx += y;
+      }
+      wtot[threadIdx.x] = sx - t;
+    }
+    __syncthreads();
+    const uint32_t excl = carry_s + wtot[threadIdx.x >> 5] + x - v;
+    if (i < n) sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+// in-place exclusive scan of one chunk + the chunk's offset
+__global__ void __launch_bounds__(256) scan_apply_kernel(uint32_t* __restrict__ data, unsigned long long n,
+                                                         const uint32_t* __restrict__ block_sums) {
+  const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_CHUNK + (unsigned long long)threadIdx.x * 16;
+  uint32_t v[16], t = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) { v[i] = base + i < n ? data[base + i] : 0u; t += v[i]; }
+  uint32_t x = t;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  __shared__ uint32_t ws[8];
+  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+  __syncthreads();
+  uint32_t off = block_sums[blockIdx.x] + x - t;
+  for (int i = 0; i < (int)(threadIdx.x >> 5); i++) off += ws[i];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if (base + i < n) data[base + i] = off;
+    off += v[i];
+  }
+}
+
+__global__ void stitch_emit_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ recs,
+                                   const unsigned long long* __restrict__ stamps, unsigned long long cap,
+                                   unsigned int special, const uint32_t* __restrict__ prefix, JunctionOut* __restrict__ out) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= cap;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[i];
+    const bool occ = i == cap ? special != 0 : key != KEY_EMPTY;
     if (!occ) continue;
-    // one atomic per warp
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+    const unsigned long long stamp = stamps[i];
+    const unsigned long long rank = (unsigned long long)prefix[stamp >> 20] + (stamp & 0xfffffull);
     const uint32_t* r = recs + i * REC_WORDS;
     JunctionOut jo;
     jo.kmer = key;
     for (int f = 0; f < 5; f++) { jo.dist[f] = (uint8_t)r[REC_DIST + f]; jo.linked[f] = (r[REC_LINK] >> f) & 1u; }
     for (int f = 0; f < 4; f++) jo.cov[f] = (uint8_t)(r[REC_COV + f] > 255u ? 255u : r[REC_COV + f]);
     jo.pad[0] = jo.pad[1] = 0;
-    jo.stamp = stamps[i];
-    out[o] = jo;
+    jo.rank = rank;
+    out[rank] = jo;
   }
 }
 

@@ -103,7 +103,7 @@ int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, 
 void faucet_gpu_free(void* p);
 
 /* ---- tuning / introspection -------------------------------------------------------------- */
-/* bytes of read text per pipelined device batch (default 128 MiB; tests use tiny values to exercise the
+/* bytes of read text per pipelined device batch (default 256 MiB, ramping up from 32 MiB; tests use tiny values to exercise the
  * multi-batch path) and the timestamp epoch length (default 2^32-2) */
 int faucet_gpu_set_batch_bytes(size_t bytes);
 int faucet_gpu_set_epoch_limit(uint64_t stamps);

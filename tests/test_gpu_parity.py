@@ -84,7 +84,7 @@ def test_load_multibatch_and_epochs(fb, oracle, small_fq):
         fb.set_epoch_limit(500_000)
         g2, g1, gst = fb.load_two_filters_mem(text, True, 31, lt, nh, want_bloo1=True)
     finally:
-        fb.set_batch_bytes(128 << 20)
+        fb.set_batch_bytes(256 << 20)
         fb.set_epoch_limit(0xfffffffe)
     assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
     assert gst.kmers == ost.kmers and gst.reads_processed == ost.reads_processed
@@ -119,7 +119,7 @@ def test_scan_fasta_spacers_multibatch(fb, oracle, small_fa):
         fb.set_batch_bytes(150_000)
         grecs, gst = fb.scan_mem(text, False, False, 1, k, 1, 40, b2, lt, nh)
     finally:
-        fb.set_batch_bytes(128 << 20)
+        fb.set_batch_bytes(256 << 20)
     assert gst == ost
     assert _strip(grecs) == _strip(orecs)
 
@@ -204,7 +204,7 @@ def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs):
     finally:
         for name, v in defaults.items():
             fb.set_tuning(name, v)
-        fb.set_batch_bytes(128 << 20)
+        fb.set_batch_bytes(256 << 20)
     assert gst == ost
     assert _strip(grecs) == _strip(orecs)
     assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
