@@ -125,32 +125,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
     const bool has_prev = V && (lane ? !((lo >> (lane - 1)) & 1u) : (w && !(__ldg(a.inval + w - 1) >> 31)));
     const uint32_t real_f = has_next ? code_at(a.packed, p + k) : 0u;
     const uint32_t real_b = has_prev ? nt_comp(code_at(a.packed, p - 1)) : 0u;
-    // ---- stage 1: first probe of the six alternates (t = 0..2 FORWARD, 3..5 BACKWARD, nucleotide order)
-    uint32_t my_idx = 0;   // 6 x 5 bits... queue index does not fit: keep one byte per alternate in two words
-    uint32_t my_idx_hi = 0;
-    uint32_t survived = 0;  // bit t: alternate t is queued
+    // ---- stage 1: first probe of the six alternates (t = 0..2 FORWARD, 3..5 BACKWARD, nucleotide order).
+    // All six canonical forms, hashes and probe loads are issued before the first one is consumed.
+    uint32_t my_idx = 0, my_idx_hi = 0;  // queue index of alternate t, one byte each
+    uint32_t survived = 0;               // bit t: alternate t is queued
     int n1 = 0;
+    uint64_t cn[6], hh[6];
+    uint32_t wd[6];
+    uint32_t cn_is_y = 0;
 #pragma unroll
     for (int t = 0; t < 6; t++) {
       const bool fdir = t < 3;
-      const bool act = fdir ? has_next : has_prev;
       const uint32_t real = fdir ? real_f : real_b;
       const uint32_t tt = fdir ? t : t - 3;
       const uint32_t c = tt < real ? tt : tt + 1;  // the tt-th nucleotide that is not the real extension
-      bool hit = false;
-      uint64_t cn = 0, h = 0;
-      bool cn_is_y = false;
-      if (act) {
-        const uint64_t y = ext_fwd(fdir ? fwd : rc, c, mask), yr = ext_rc(fdir ? rc : fwd, c, k);
-        cn_is_y = y < yr;
-        cn = cn_is_y ? y : yr;
-        h = hash0(cn) & a.tai_mask;
-        hit = bloom_bit(a, h);
-      }
+      const uint64_t y = ext_fwd(fdir ? fwd : rc, c, mask), yr = ext_rc(fdir ? rc : fwd, c, k);
+      cn_is_y |= (y < yr ? 1u : 0u) << t;
+      cn[t] = y < yr ? y : yr;
+      hh[t] = hash0(cn[t]) & a.tai_mask;
+      wd[t] = (fdir ? has_next : has_prev) ? __ldg(a.bloom + (hh[t] >> 5)) : 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+      const bool hit = (wd[t] >> (hh[t] & 31)) & 1u;
       const uint32_t b = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int e = n1 + __popc(b & lt_mask);
-        q.canon[e] = cn; q.h0[e] = h; q.tag[e] = cn_is_y ? 1 : 0;
+        q.canon[e] = cn[t]; q.h0[e] = hh[t]; q.tag[e] = (cn_is_y >> t) & 1u;
         survived |= 1u << t;
         if (t < 4) my_idx |= (uint32_t)e << (8 * t); else my_idx_hi |= (uint32_t)e << (8 * (t - 4));
       }
