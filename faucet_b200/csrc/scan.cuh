@@ -65,6 +65,23 @@ __device__ __forceinline__ bool bloom_contains(const ScanArgs& a, uint64_t x, ui
   return true;
 }
 
+// same answer with every probe in flight at once (no early exit): for k-mers that are mostly members
+template <int NH>
+__device__ __forceinline__ bool bloom_contains_all(const ScanArgs& a, uint64_t x, uint64_t xrc) {
+  const int nh = NH ? NH : a.n_hash;
+  const uint64_t c = canon(x, xrc);
+  uint64_t h = hash0(c) & a.tai_mask;
+  const uint64_t h1 = hash1(c) & a.tai_mask;
+  uint32_t ok = 1u;
+#pragma unroll
+  for (int i = 0; i < (NH ? NH : MAX_NHASH); i++) {
+    if (i >= nh) break;
+    ok &= __ldg(a.bloom + (h >> 5)) >> (h & 31);
+    h = (h + h1) & a.tai_mask;
+  }
+  return ok & 1u;
+}
+
 // JChecker::jcheck(kmer_type), utils/JChecker.cpp:51-80: true iff some path of j Bloom-positive
 // forward extensions leaves x.  (Depth-first with early exit; the BFS there computes the same bool.)
 template <int NH>
@@ -118,7 +135,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
     if (start_ok) {
       fwd = kmer_at(a.packed, p, k);
       rc = revcomp(fwd, k);
-      V = bloom_contains<NH>(a, fwd, rc);
+      V = bloom_contains_all<NH>(a, fwd, rc);
     }
     // FORWARD half-step needs read[p+k]; BACKWARD needs read[p-1] (utils/ReadKmer.cpp:107-114)
     const bool has_next = V && !((win >> k) & 1ull);
@@ -168,12 +185,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
         if (nh > 1) {
           const uint64_t h1 = hash1(q.canon[e]) & a.tai_mask;
           uint64_t h = q.h0[e];
+          uint32_t ok = 1u;
 #pragma unroll
-          for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {
+          for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {  // all remaining probes in flight together
             if (i >= nh) break;
             h = (h + h1) & a.tai_mask;
-            if (!bloom_bit(a, h)) { full = false; break; }
+            ok &= __ldg(a.bloom + (h >> 5)) >> (h & 31);
           }
+          full = ok & 1u;
         }
         q.res[e] = full ? (a.j == 0 ? 3 : 1) : 0;
       }
