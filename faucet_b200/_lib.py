@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libfaucet_gpu.so")
+_SO = os.environ.get("FAUCET_GPU_LIB") or os.path.join(_HERE, "libfaucet_gpu.so")  # override: kernel experiments only
 
 
 class FaucetError(RuntimeError):

@@ -604,7 +604,11 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   if (!s->stitch_grid) {
     int per_sm = 0;
     const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
+#if FAUCET_STITCH_THREADS >= 512
+    s->stitch_fn = (const void*)stitch_kernel<1>;
+#else
     s->stitch_fn = g.stitch_blocks == 4 ? (const void*)stitch_kernel<4> : g.stitch_blocks == 3 ? (const void*)stitch_kernel<3> : (const void*)stitch_kernel<2>;
+#endif
     CU(cudaFuncSetAttribute(s->stitch_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->stitch_fn, STITCH_THREADS, smem));
     if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_kernel cannot be made resident");

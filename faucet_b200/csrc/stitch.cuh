@@ -46,7 +46,10 @@ namespace faucet {
 
 namespace cg = cooperative_groups;
 
-constexpr int STITCH_THREADS = 256;
+#ifndef FAUCET_STITCH_THREADS
+#define FAUCET_STITCH_THREADS 256
+#endif
+constexpr int STITCH_THREADS = FAUCET_STITCH_THREADS;
 constexpr int STITCH_WARPS = STITCH_THREADS / 32;
 constexpr unsigned long long KEY_EMPTY = ~0ull;
 constexpr uint32_t RES_FREE = 0xffffffffu;
