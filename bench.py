@@ -29,6 +29,9 @@ WORKLOADS = {
                desc="synthetic E. coli-sized 4.6 Mbp genome, 100x 150bp paired-end, k=31, --two_hash"),
     "c3": dict(genome=64_000_000, cov=50, length=100, insert=300, k=27, est=64_000_000, sing=20_000_000,
                desc="synthetic 64 Mbp (chr20-sized) genome, 50x 100bp paired-end, k=27"),
+    # configs[3]: 1 Gbp of reads against a filter sized for 1e9 k-mers: 1 GiB Bloom arrays, the HBM-resident case
+    "c4": dict(genome=100_000_000, cov=10, length=100, insert=300, k=31, est=1_000_000_000, sing=200_000_000,
+               desc="synthetic 1 Gbp read stream (100 Mbp genome, 10x, 100bp PE), -estimated_kmers 1e9 -singletons 2e8, k=31"),
 }
 J, MAX_SPACER, FP = 1, 100, 0.04  # faucet defaults: -j 1, -max_spacer_dist 100, -fp 0.04 (src/Faucet.h:14-48)
 

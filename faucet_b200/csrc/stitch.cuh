@@ -540,9 +540,9 @@ __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
 }
 
 // phase 1: everything the walk will want to know about the line, all loads in flight together
+template <int PF>  // positions per lane per pass
 __device__ void prefetch_line(const StitchArgs& a, WarpScratch* S, uint32_t ls, int n_pos, int lane) {
   const int k = a.k;
-  constexpr int PF = 2;  // positions per lane per pass
   for (int base = 0; base < n_pos; base += 32 * PF) {
     uint64_t fwd[PF], rcv[PF];
     unsigned long long kf[PF], kb[PF];
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
         const unsigned long long ta = gtime_ns();
         line_reservations<0, true>(a, S->pk, ls & 15u, len, rec, lane, S->reskey, &n_res);
         const unsigned long long tb = gtime_ns();
-        prefetch_line(a, S, ls, n_pos, lane);
+        prefetch_line<(MIN_BLOCKS >= 4 ? 1 : 2)>(a, S, ls, n_pos, lane);
         if (gw == 0 && lane == 0) { c.S->st[SS_T_P1A] += ta - t0; c.S->st[SS_T_P1B] += tb - ta; c.S->st[SS_T_P1C] += gtime_ns() - tb; }
       } else {
         line_reservations<0, false>(a, a.packed, ls, len, rec, lane, S->reskey, &n_res);
