@@ -99,11 +99,11 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(workload, kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p)).get(kernel, {}).get("bytes")
+        return json.load(open(p)).get(workload, {}).get(kernel, {}).get("bytes")
     except (OSError, ValueError):
         return None
 
@@ -332,7 +332,7 @@ def run_ours(args, w):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom), "peak_kind": peak_kind,
                          "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms},
             "kernels_ms_per_step": {n: v[0] / args.steps for n, v in kernel_ms.items()},
             "bloom_weight2": weight2, "contained_fraction": r_contained, "stitch": stitch_info,

@@ -217,6 +217,7 @@ int faucet_gpu_init(int device) {
   CU(cudaGetDeviceProperties(&prop, device));
   g.sm_count = prop.multiProcessorCount;
   g.device = device;
+
   g.inited = true;
   return 0;
 }
