@@ -283,7 +283,7 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
                           size_t max_text_bytes) {
   if (!g.inited) { int rc = faucet_gpu_init(0); if (rc) return rc; }
   if (k < 2 || k > 32) return fail(FAUCET_E_ARG, "k must be in [2,32]");
-  if (log2_tai < 6 || log2_tai > 40) return fail(FAUCET_E_ARG, "log2_tai must be in [6,40]");
+  if (log2_tai < 6 || log2_tai > 37) return fail(FAUCET_E_ARG, "log2_tai must be in [6,37]");  // word index in 32 bits
   if (n_hash < 1 || n_hash > MAX_NHASH) return fail(FAUCET_E_ARG, "n_hash must be in [1,10]");
   if (j < 0 || j > MAX_J) return fail(FAUCET_E_ARG, "j must be in [0,4]");
   if (max_text_bytes > ((size_t)3 << 30)) return fail(FAUCET_E_ARG, "a batch must stay below 3 GiB");
@@ -552,7 +552,7 @@ int faucet_session_scan_flags(faucet_session* s) {
   if (rc) return rc;
   ScanArgs a;
   a.inval = s->d_inval; a.packed = s->d_packed; a.n_words = (uint32_t)((s->n + 31) / 32);
-  a.bloom = s->d_bloom; a.tai_mask = s->tai() - 1; a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
+  a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
   const int grid = g.sm_count * 8;
   {
     KTimer kt(s, KT_SCAN);

@@ -49,12 +49,38 @@ FHD uint64_t ext_rc(uint64_t rc, uint32_t nt, int k) { return (rc >> 2) | ((uint
 #define FAUCET_SEED1 0x1140aada557088a4ull
 
 // Bloom::oldHash before masking, utils/Bloom.h:134-145.  Everything that depends only on the seed
-// is folded at compile time.
+// is folded at compile time.  The reference spells the mixing rounds as shift-adds; on the device they
+// are written as what they are -- multiplications by constants (h + (h<<3) + (h<<8) = 265 h, ...) and
+// xor-shifts whose high word is a multiply-high by a power of two -- so that ptxas emits IMAD /
+// IMAD.WIDE / IMAD.HI on the fma pipe instead of LEA / SHF chains on the alu pipe: the kernels that hash
+// are integer-issue bound and the alu pipe was the busy one (34 of 41 instructions -> 18 of 35).
+#ifndef FAUCET_HASH_VARIANT
+#define FAUCET_HASH_VARIANT 2
+#endif
+FHD uint64_t xorshr(uint64_t h, int s) {  // h ^ (h >> s), 0 < s < 32
+#if defined(__CUDA_ARCH__) && FAUCET_HASH_VARIANT >= 2
+  const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+  const uint32_t hs = __umulhi(hi, 1u << (32 - s));  // == hi >> s
+  const uint32_t ls = __funnelshift_r(lo, hi, s);
+  return ((uint64_t)(hi ^ hs) << 32) | (lo ^ ls);
+#else
+  return h ^ (h >> s);
+#endif
+}
 template <uint64_t SEED>
 FHD uint64_t old_hash(uint64_t key) {
   constexpr uint64_t s7 = SEED ^ (SEED << 7);
   constexpr uint64_t s3 = SEED >> 3, s11 = SEED << 11, s5 = SEED >> 5;
   uint64_t h = s7 ^ (key * s3) ^ (~(s11 + (key ^ s5)));
+#if defined(__CUDA_ARCH__) && FAUCET_HASH_VARIANT >= 1
+  h = h * 0x1fffffull - 1ull;  // (~h) + (h << 21)
+  h = xorshr(h, 24);
+  h = h * 265ull;              // (h + (h << 3)) + (h << 8)
+  h = xorshr(h, 14);
+  h = h * 21ull;               // (h + (h << 2)) + (h << 4)
+  h = xorshr(h, 28);
+  h = h * 0x80000001ull;       // h + (h << 31)
+#else
   h = (~h) + (h << 21);
   h = h ^ (h >> 24);
   h = (h + (h << 3)) + (h << 8);
@@ -62,6 +88,7 @@ FHD uint64_t old_hash(uint64_t key) {
   h = (h + (h << 2)) + (h << 4);
   h = h ^ (h >> 28);
   h = h + (h << 31);
+#endif
   return h;
 }
 FHD uint64_t hash0(uint64_t key) { return old_hash<FAUCET_SEED0>(key); }

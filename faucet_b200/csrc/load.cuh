@@ -81,7 +81,7 @@ __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uin
   for (int i = 0; i < (NH ? NH : MAX_NHASH); i++)
     if (i < nh) {
       pos[i] = (h0 + (uint64_t)i * h1) & a.tai_mask;
-      wd[i] = a.fused[pos[i] >> 5];
+      wd[i] = a.fused[(uint32_t)(pos[i] >> 5)];  // 32-bit word index (log2_tai <= 37): one IMAD.WIDE address
     }
   bool all1 = true;
 #pragma unroll
@@ -92,7 +92,7 @@ __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uin
 #pragma unroll
     for (int i = 0; i < (NH ? NH : MAX_NHASH); i++)
       if (i < nh && !((wd[i] >> (32 + (pos[i] & 31))) & 1ull))
-        atomicOr(reinterpret_cast<unsigned int*>(a.fused) + 2 * (pos[i] >> 5) + 1, 1u << (pos[i] & 31));
+        atomicOr(reinterpret_cast<unsigned int*>(a.fused + (uint32_t)(pos[i] >> 5)) + 1, 1u << (pos[i] & 31));
     return false;
   }
 #pragma unroll
@@ -124,7 +124,7 @@ __device__ __forceinline__ bool load_body_B(const LoadArgs& a, uint64_t fwd, uin
   const int half = contained ? 1 : 0;  // bloo2 if contained, bloo1 otherwise (utils/Bloom.cpp:293-298)
 #pragma unroll
   for (int i = 0; i < (NH ? NH : MAX_NHASH); i++)
-    if (i < nh) atomicOr(reinterpret_cast<unsigned int*>(a.fused) + 2 * (pos[i] >> 5) + half, 1u << (pos[i] & 31));
+    if (i < nh) atomicOr(reinterpret_cast<unsigned int*>(a.fused + (uint32_t)(pos[i] >> 5)) + half, 1u << (pos[i] & 31));
   return contained;
 }
 

@@ -39,13 +39,19 @@ struct ScanArgs {
   const uint32_t* packed;
   uint32_t n_words;
   const uint32_t* bloom;  // bloo2, plain reference layout viewed as little-endian u32 words
-  uint64_t tai_mask;
+  uint32_t wmask;         // (tai - 1) >> 5: word index mask (log2_tai <= 37, checked by the session)
   int k, j, n_hash;
   uint8_t* flags;
 };
 
+// Word holding bit (h mod tai).  Hash values are carried UNMASKED: (h0 + i*h1) mod tai only needs the
+// low log2_tai bits of the 64-bit sum, so masking happens once, on the 32-bit word index (one funnel
+// shift + one and + one IMAD.WIDE for the address instead of 64-bit shift/mask/add chains).
+__device__ __forceinline__ uint32_t bloom_word(const ScanArgs& a, uint64_t h) {
+  return __ldg(a.bloom + (__funnelshift_r((uint32_t)h, (uint32_t)(h >> 32), 5) & a.wmask));
+}
 __device__ __forceinline__ bool bloom_bit(const ScanArgs& a, uint64_t h) {
-  return (__ldg(a.bloom + (h >> 5)) >> (h & 31)) & 1u;
+  return (bloom_word(a, h) >> ((uint32_t)h & 31u)) & 1u;
 }
 
 // Bloom::oldContains -> contains(h0,h1), utils/Bloom.h:162-173,242-258 (early exit on a clear bit)
@@ -53,13 +59,13 @@ template <int NH>
 __device__ __forceinline__ bool bloom_contains(const ScanArgs& a, uint64_t x, uint64_t xrc) {
   const int nh = NH ? NH : a.n_hash;
   uint64_t c = canon(x, xrc);
-  uint64_t h = hash0(c) & a.tai_mask;
+  uint64_t h = hash0(c);
   if (!bloom_bit(a, h)) return false;
-  uint64_t h1 = hash1(c) & a.tai_mask;
+  const uint64_t h1 = hash1(c);
 #pragma unroll
   for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {
     if (i >= nh) break;
-    h = (h + h1) & a.tai_mask;
+    h += h1;
     if (!bloom_bit(a, h)) return false;
   }
   return true;
@@ -70,14 +76,14 @@ template <int NH>
 __device__ __forceinline__ bool bloom_contains_all(const ScanArgs& a, uint64_t x, uint64_t xrc) {
   const int nh = NH ? NH : a.n_hash;
   const uint64_t c = canon(x, xrc);
-  uint64_t h = hash0(c) & a.tai_mask;
-  const uint64_t h1 = hash1(c) & a.tai_mask;
+  uint64_t h = hash0(c);
+  const uint64_t h1 = hash1(c);
   uint32_t ok = 1u;
 #pragma unroll
   for (int i = 0; i < (NH ? NH : MAX_NHASH); i++) {
     if (i >= nh) break;
-    ok &= __ldg(a.bloom + (h >> 5)) >> (h & 31);
-    h = (h + h1) & a.tai_mask;
+    ok &= bloom_word(a, h) >> ((uint32_t)h & 31u);
+    h += h1;
   }
   return ok & 1u;
 }
@@ -159,12 +165,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
       const uint64_t y = ext_fwd(fdir ? fwd : rc, c, mask), yr = ext_rc(fdir ? rc : fwd, c, k);
       cn_is_y |= (y < yr ? 1u : 0u) << t;
       cn[t] = y < yr ? y : yr;
-      hh[t] = hash0(cn[t]) & a.tai_mask;
-      wd[t] = (fdir ? has_next : has_prev) ? __ldg(a.bloom + (hh[t] >> 5)) : 0u;
+      hh[t] = hash0(cn[t]);
+      wd[t] = (fdir ? has_next : has_prev) ? bloom_word(a, hh[t]) : 0u;
     }
 #pragma unroll
     for (int t = 0; t < 6; t++) {
-      const bool hit = (wd[t] >> (hh[t] & 31)) & 1u;
+      const bool hit = (wd[t] >> ((uint32_t)hh[t] & 31u)) & 1u;
       const uint32_t b = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int e = n1 + __popc(b & lt_mask);
@@ -183,14 +189,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
       if (e < n1) {
         full = true;
         if (nh > 1) {
-          const uint64_t h1 = hash1(q.canon[e]) & a.tai_mask;
+          const uint64_t h1 = hash1(q.canon[e]);
           uint64_t h = q.h0[e];
           uint32_t ok = 1u;
 #pragma unroll
           for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {  // all remaining probes in flight together
             if (i >= nh) break;
-            h = (h + h1) & a.tai_mask;
-            ok &= __ldg(a.bloom + (h >> 5)) >> (h & 31);
+            h += h1;
+            ok &= bloom_word(a, h) >> ((uint32_t)h & 31u);
           }
           full = ok & 1u;
         }
