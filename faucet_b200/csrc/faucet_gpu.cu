@@ -16,6 +16,7 @@
 #include "scan.cuh"
 #include "pair_filter_host.hpp"
 #include "stitch.cuh"
+#include "stitch2.cuh"
 
 using namespace faucet;
 
@@ -32,6 +33,8 @@ struct Global {
   int res_log2 = 24;                           // reservation table entries (u32 each)
   uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048, stitch_shrink_den = 4, stitch_grow_den = 10;
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
+  int stitch_impl = 2;    // 2: one thread per record (stitch2.cuh); 1: one warp per record (stitch.cuh)
+  size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
   unsigned long long ext_cap0 = 1ull << 24;
   size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
   faucet_timings tim{};
@@ -106,6 +109,9 @@ struct faucet_session {
   std::vector<faucet_junction_rec> recs_out;
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
+  int impl = 0;                 // stitch kernel this session's flag buffer is laid out for (g.stitch_impl at creation)
+  uint32_t* d_rows = nullptr;   // stitch2: reservation rows of the records [row_base, row_end)
+  size_t rows_cap = 0;
   uint32_t *d_hist = nullptr, *d_hist_sums = nullptr;  // junction-creation counts per record (ordering)
   unsigned long long hist_cap = 0;
   faucet_junction_rec* d_out = nullptr;
@@ -257,6 +263,12 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "stitch_blocks") {
     if (value < 2 || value > 4) return fail(FAUCET_E_ARG, "stitch_blocks must be 2, 3 or 4");
     g.stitch_blocks = (int)value;
+  } else if (n == "stitch_impl") {
+    if (value != 1 && value != 2) return fail(FAUCET_E_ARG, "stitch_impl must be 1 (warp per record) or 2 (thread per record)");
+    g.stitch_impl = (int)value;
+  } else if (n == "rows_max") {
+    if (value < 1 || value > ((uint64_t)1 << 26)) return fail(FAUCET_E_ARG, "rows_max out of range");
+    g.rows_max = (size_t)value;
   } else if (n == "stitch_w0") {
     if (value < 1) return fail(FAUCET_E_ARG, "stitch_w0 out of range");
     g.stitch_w0 = (uint32_t)value;
@@ -289,6 +301,7 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   if (max_text_bytes > ((size_t)3 << 30)) return fail(FAUCET_E_ARG, "a batch must stay below 3 GiB");
   faucet_session* s = new faucet_session();
   s->k = k; s->log2_tai = log2_tai; s->n_hash = n_hash; s->j = j; s->max_spacer = max_spacer_dist;
+  s->impl = g.stitch_impl;
   s->cap = ((max_text_bytes + TAIL_MAX + PARSE_CHUNK - 1) / PARSE_CHUNK) * PARSE_CHUNK;
   int rc = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -327,7 +340,7 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
-  cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
+  cudaFree(s->d_rows); cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
   cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   faucet_session_close_peers(s);
@@ -553,6 +566,7 @@ int faucet_session_scan_flags(faucet_session* s) {
   ScanArgs a;
   a.inval = s->d_inval; a.packed = s->d_packed; a.n_words = (uint32_t)((s->n + 31) / 32);
   a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
+  a.fplanes = s->impl == 2 ? reinterpret_cast<uint32_t*>(s->d_flags) : nullptr;
   const int grid = g.sm_count * 8;
   {
     KTimer kt(s, KT_SCAN);
@@ -602,6 +616,15 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     CU(cudaMemsetAsync(s->d_recs, 0, (s->tbl_cap + 1) * REC_WORDS * 4, s->stream));
   }
   s->w_max = g.stitch_w_max;
+  if (!s->stitch_grid && s->impl == 2) {
+    int per_sm = 0;
+    const size_t smem = S2_WARPS * sizeof(WarpScratch);
+    s->stitch_fn = (const void*)stitch2_kernel;
+    CU(cudaFuncSetAttribute(s->stitch_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->stitch_fn, S2_THREADS, smem));
+    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch2_kernel cannot be made resident");
+    s->stitch_grid = g.sm_count;  // one CTA per SM: the cheapest grid barrier
+  }
   if (!s->stitch_grid) {
     int per_sm = 0;
     const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
@@ -615,8 +638,8 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_kernel cannot be made resident");
     s->stitch_grid = per_sm * g.sm_count;
   }
-  // one record per warp per round
-  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * STITCH_WARPS);
+  // one record per warp (thread) per round
+  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * (s->impl == 2 ? S2_THREADS : STITCH_WARPS));
   if (!s->d_res) {
     if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
@@ -665,9 +688,23 @@ int faucet_session_stitch_batch(faucet_session* s) {
   struct { unsigned int next, nd[2]; } z = {0, {0, 0}};
   CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
   s->h_ext.clear();
+  uint32_t row_base = 0, row_end = s->n_recs;
+  bool rows_ready = false;
+  if (s->impl == 2) {
+    row_end = (uint32_t)std::min<size_t>(s->n_recs, g.rows_max);
+    const size_t need = std::max<size_t>(1, row_end);
+    if (need > s->rows_cap) {
+      cudaFree(s->d_rows); s->d_rows = nullptr;
+      int rc = dmalloc(&s->d_rows, need * S2_ROW);
+      if (rc) return rc;
+      s->rows_cap = need;
+    }
+  }
   while (true) {
     StitchArgs a;
-    a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->d_flags;
+    a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->impl == 2 ? nullptr : s->d_flags;
+    a.fplanes = s->impl == 2 ? reinterpret_cast<const uint32_t*>(s->d_flags) : nullptr;
+    a.rows = s->d_rows; a.row_base = row_base; a.row_end = row_end;
     a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
     a.k = s->k; a.j = s->j; a.spacer = s->max_spacer; a.no_cleaning = s->no_cleaning; a.paired = s->paired;
     a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
@@ -681,8 +718,18 @@ int faucet_session_stitch_batch(faucet_session* s) {
     void* params[] = {&a};
     {
       KTimer kt(s, KT_STITCH);
-      CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(STITCH_THREADS), params,
-                                     STITCH_WARPS * sizeof(WarpScratch), s->stream));
+      if (s->impl == 2) {
+        if (!rows_ready && row_end > row_base) {  // pure function of the text: the minimizer slots of every record
+          stitch2_rows_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(a, s->d_rows);
+          s->launches++;
+          rows_ready = true;
+        }
+        CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(S2_THREADS), params,
+                                       S2_WARPS * sizeof(WarpScratch), s->stream));
+      } else {
+        CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(STITCH_THREADS), params,
+                                       STITCH_WARPS * sizeof(WarpScratch), s->stream));
+      }
       s->launches++;
     }
     unsigned int status = 0;
@@ -691,9 +738,14 @@ int faucet_session_stitch_batch(faucet_session* s) {
     int rc = check_launch("stitch");
     if (rc) return rc;
     if (status == ST_DONE) break;
+    if (status == ST_STUCK) return fail(FAUCET_E_CUDA, "stitch: a round executed no record (internal error)");
     // an aborted round leaves its reservations behind
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
-    if (status == ST_GROW_TABLE) {
+    if (status == ST_MORE_ROWS) {  // every record of [row_base, row_end) is done: list the next ones
+      row_base = row_end;
+      row_end = (uint32_t)std::min<size_t>(s->n_recs, (size_t)row_base + g.rows_max);
+      rows_ready = false;
+    } else if (status == ST_GROW_TABLE) {
       if ((rc = stitch_grow_table(s))) return rc;
     } else if (status == ST_DRAIN_EXT) {
       unsigned long long used = 0;
@@ -919,7 +971,7 @@ int faucet_session_import_planes(faucet_session* s, int peer_rank, size_t n_text
     const size_t words = (n_text + 31) / 32 + 2;
     CU(cudaMemcpyAsync(s->d_inval, s->peer[FAUCET_BUF_INVAL][peer_rank], words * 4, cudaMemcpyDeviceToDevice, s->stream));
     CU(cudaMemcpyAsync(s->d_packed, s->peer[FAUCET_BUF_PACKED][peer_rank], (2 * words + 2) * 4, cudaMemcpyDeviceToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->d_flags, s->peer[FAUCET_BUF_FLAGS][peer_rank], n_text, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_flags, s->peer[FAUCET_BUF_FLAGS][peer_rank], (words - 2) * 32, cudaMemcpyDeviceToDevice, s->stream));  // bytes or 8 plane words per 32
     CU(cudaMemcpyAsync(s->d_seq_start, s->peer[FAUCET_BUF_SEQ_START][peer_rank], (size_t)n_recs * 4, cudaMemcpyDeviceToDevice, s->stream));
     CU(cudaMemcpyAsync(s->d_seq_end, s->peer[FAUCET_BUF_SEQ_END][peer_rank], (size_t)n_recs * 4, cudaMemcpyDeviceToDevice, s->stream));
   }

@@ -41,7 +41,8 @@ struct ScanArgs {
   const uint32_t* bloom;  // bloo2, plain reference layout viewed as little-endian u32 words
   uint32_t wmask;         // (tai - 1) >> 5: word index mask (log2_tai <= 37, checked by the session)
   int k, j, n_hash;
-  uint8_t* flags;
+  uint8_t* flags;     // one byte per byte offset (warp-per-record stitch) ...
+  uint32_t* fplanes;  // ... or, when not NULL, the same bits transposed: word w of plane i (= bit i) at fplanes[8 w + i]
 };
 
 // Word holding bit (h mod tai).  Hash values are carried UNMASKED: (h0 + i*h1) mod tai only needs the
@@ -133,7 +134,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
     const uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
     const uint64_t win = inval_window(lo, hi, lane);
     const bool start_ok = (win & kbits) == 0;
-    if (!__any_sync(0xffffffffu, start_ok)) continue;
+    if (!__any_sync(0xffffffffu, start_ok)) {
+      if (a.fplanes && lane < 8) a.fplanes[(size_t)w * 8 + lane] = 0u;
+      continue;
+    }
     const uint32_t p = (w << 5) + lane;
     // ---- stage 0
     uint64_t fwd = 0, rc = 0;
@@ -233,8 +237,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
     }
     __syncwarp();
     // ---- stage 4: testForJunction's early exit, in nucleotide order (src/ReadScanner.cpp:41-53)
+    uint32_t f = 0;
     if (start_ok) {
-      uint32_t f = V ? 1u : 0u;
+      f = V ? 1u : 0u;
 #pragma unroll
       for (int d = 0; d < 2; d++) {
         uint32_t cnt = 0, junc = 0;
@@ -250,7 +255,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
         }
         f |= d == 0 ? (junc << 1) | (cnt << 3) : (junc << 2) | (cnt << 5);
       }
-      a.flags[p] = (uint8_t)f;
+      if (!a.fplanes) a.flags[p] = (uint8_t)f;
+    }
+    if (a.fplanes) {  // 7 ballots transpose the warp's 32 flag bytes into one 32-byte group of plane words
+      uint32_t mine = 0;
+#pragma unroll
+      for (int i = 0; i < 7; i++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (f >> i) & 1u);
+        if (lane == i) mine = b;
+      }
+      if (lane < 8) a.fplanes[(size_t)w * 8 + lane] = mine;
     }
     __syncwarp();  // the queues are reused by the next word
   }

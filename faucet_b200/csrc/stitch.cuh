@@ -60,7 +60,7 @@ constexpr int VIS_CAP = 32;     // junction slots a line touched (beyond it ever
 constexpr int REC_WORDS = 16;   // u32 per junction record
 enum { REC_DIST = 0, REC_LINK = 5, REC_COV = 6 };
 
-enum { ST_DONE = 0, ST_GROW_TABLE = 1, ST_DRAIN_EXT = 2 };
+enum { ST_DONE = 0, ST_GROW_TABLE = 1, ST_DRAIN_EXT = 2, ST_MORE_ROWS = 3, ST_STUCK = 4 };
 enum { SS_JCHECK = 0, SS_NOJUNC, SS_PROCESSED, SS_SKIPPED, SS_NOERR, SS_UNAMBIG, SS_ROUNDS, SS_DEFERRED,
        SS_T_PHASE1, SS_T_SYNC1, SS_T_PHASE2, SS_T_SYNC2, SS_T_P1A, SS_T_P1B, SS_T_P1C, SS_T_P2A, SS_COUNT };  // SS_T_*: ns seen by warp 0 of the grid
 
@@ -80,7 +80,10 @@ struct StitchState {             // device-resident; survives kernel launches an
 struct StitchArgs {
   const uint32_t* inval;
   const uint32_t* packed;
-  const uint8_t* flags;
+  const uint8_t* flags;           // scan_flags output, one byte per k-mer start (warp-per-record kernel) ...
+  const uint32_t* fplanes;        // ... or the same bits as 8 interleaved planes (thread-per-record kernel, stitch2.cuh)
+  const uint32_t* rows;           // stitch2: reservation slots of record r at rows[32 (r - row_base)] (count, then slots)
+  uint32_t row_base, row_end;     // stitch2: records [row_base, row_end) have rows
   const uint32_t* seq_start;
   const uint32_t* seq_end;
   uint32_t n_recs;               // records in this batch
@@ -147,6 +150,16 @@ __device__ __forceinline__ uint32_t code_at_t(const uint32_t* packed, uint32_t p
   return (ldw<SH>(packed + (p >> 4)) >> (30 - 2 * (p & 15))) & 3u;
 }
 
+// scan_flags byte of byte offset p, from whichever form the batch holds (plane i = bit i of the byte)
+__device__ __forceinline__ uint32_t flag_byte(const StitchArgs& a, uint32_t p) {
+  if (a.flags) return a.flags[p];
+  const uint32_t* w = a.fplanes + (size_t)(p >> 5) * 8;
+  uint32_t f = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) f |= ((__ldg(w + i) >> (p & 31)) & 1u) << i;
+  return f;
+}
+
 // h(canonical s-mer starting at byte offset q), s <= 16
 template <bool SH>
 __device__ __forceinline__ uint32_t smer_hash(const uint32_t* packed, uint32_t q, int s) {
@@ -166,13 +179,14 @@ __device__ __forceinline__ uint32_t shift64(uint32_t x0, uint32_t x1, int d, int
 }
 
 // One warp walks the minimizers of line [ls, ls+len): one reservation slot per run of equal values.
-// MODE 0: reserve with atomicMin and remember the slots in `keep` (*n_keep > RES_CAP: did not fit);
-// MODE 1: check (false on a foreign reservation); MODE 2: release own reservations.
+// MODE 0: reserve with atomicMin and remember the slots in `keep` (*n_keep > keep_cap: did not fit);
+// MODE 1: check (false on a foreign reservation); MODE 2: release own reservations;
+// MODE 3: only list the slots in `keep` (the reservation rows of stitch2.cuh).
 template <int MODE, bool SH>
 __device__ bool line_reservations(const StitchArgs& a, const uint32_t* packed, uint32_t ls, uint32_t len, uint32_t rec,
-                                  int lane, uint32_t* keep, int* n_keep) {
+                                  int lane, uint32_t* keep, int* n_keep, int keep_cap = RES_CAP) {
   const int k = a.k, s = k < 16 ? k : 16, w = k - s + 1;
-  if (MODE == 0) *n_keep = 0;
+  if (MODE == 0 || MODE == 3) *n_keep = 0;
   if (len < (uint32_t)k) return true;
   const uint32_t nk = len - k + 1, ns = len - s + 1;
   int lg = 0;
@@ -202,11 +216,11 @@ __device__ bool line_reservations(const StitchArgs& a, const uint32_t* packed, u
     if (lane == 0) left = prev_last;
     const bool active = base + lane < nk && (base + lane == 0 || m != left);
     uint32_t* slot = a.res + (m & a.res_mask);
-    if (MODE == 0) {
-      if (active) atomicMin(slot, rec);
+    if (MODE == 0 || MODE == 3) {
+      if (MODE == 0 && active) atomicMin(slot, rec);
       const uint32_t b = __ballot_sync(0xffffffffu, active);
       const int at = nkeep + __popc(b & ((1u << lane) - 1u));
-      if (active && at < RES_CAP) keep[at] = m & a.res_mask;
+      if (active && at < keep_cap) keep[at] = m & a.res_mask;
       nkeep += __popc(b);
     }
     if (MODE == 1 && active && __ldcg(slot) != rec) ok = false;
@@ -214,7 +228,7 @@ __device__ bool line_reservations(const StitchArgs& a, const uint32_t* packed, u
     prev_last = __shfl_sync(0xffffffffu, m, 31);
     g0 = g1;
   }
-  if (MODE == 0) *n_keep = nkeep;
+  if (MODE == 0 || MODE == 3) *n_keep = nkeep;
   return MODE == 1 ? __all_sync(0xffffffffu, ok) : true;
 }
 
@@ -240,6 +254,21 @@ __device__ __forceinline__ int tbl_insert(const StitchArgs& a, uint64_t key, boo
   while (true) {
     unsigned long long old = atomicCAS(a.keys + h, KEY_EMPTY, (unsigned long long)key);
     if (old == KEY_EMPTY) { *created = true; atomicAdd(&a.st->n_entries, 1ull); return (int)h; }
+    if (old == key) { *created = false; return (int)h; }
+    h = (h + 1) & (a.cap - 1);
+  }
+}
+// the same without touching the shared entry counter (the caller adds its creations up once per round)
+__device__ __forceinline__ int tbl_insert_nc(const StitchArgs& a, uint64_t key, bool* created) {
+  if (key == KEY_EMPTY) {
+    *created = atomicExch(&a.st->special, 1u) == 0u;
+    if (*created) a.keys[a.cap] = key;
+    return (int)a.cap;
+  }
+  uint64_t h = mix64(key) & (a.cap - 1);
+  while (true) {
+    unsigned long long old = atomicCAS(a.keys + h, KEY_EMPTY, (unsigned long long)key);
+    if (old == KEY_EMPTY) { *created = true; return (int)h; }
     if (old == key) { *created = false; return (int)h; }
     h = (h + 1) & (a.cap - 1);
   }
@@ -368,7 +397,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
         } else {
           const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
           sl = tbl_find(a, dir ? fwd : revcomp(fwd, k));
-          f = a.flags[s0 + pos];
+          f = flag_byte(a, s0 + pos);
         }
         known = sl >= 0;
         spc = t - last_junc_pos >= 2 * a.spacer - 1;
@@ -513,7 +542,7 @@ __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
     int run_start = -1;
     for (int base = 0; base <= npos; base += 32) {
       const int i = base + lane;
-      const bool v = i < npos && ((FAST ? c.S->flag[ss - ls + i] : a.flags[ss + i]) & 1u);
+      const bool v = i < npos && ((FAST ? c.S->flag[ss - ls + i] : flag_byte(a, ss + i)) & 1u);
       const uint32_t m = __ballot_sync(0xffffffffu, v);
       const int lanes = npos + 1 - base < 32 ? npos + 1 - base : 32;
       int bit = 0;

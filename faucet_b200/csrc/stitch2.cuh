@@ -1,0 +1,241 @@
+// Pass 2, stream-order part: ONE THREAD per record (the default stitch; stitch.cuh keeps the
+// warp-per-record kernel it grew out of, selectable with faucet_gpu_set_tuning("stitch_impl", 1)).
+//
+// Same schedule as stitch.cuh -- windowed deterministic reservations on minimizers, two grid barriers
+// per round, junction table in HBM -- but the per-round parallelism of that kernel was capped by "one
+// record per warp": 3.5 k records per round on a B200 while the E. coli-sized workload supports ~9 k
+// conflict-free records per round (window ~14-28 k).  Here a record is one thread:
+//   * the minimizer reservation slots of every record are a pure function of the text and are listed
+//     once per batch by stitch2_rows_kernel (one 128-byte row per record), so reserving / checking /
+//     releasing is 1-2 vector loads and <= 31 atomics per thread and no minimizer is computed inside
+//     the round loop;
+//   * phase 1: the thread looks up the FORWARD and BACKWARD key of every k-mer position of its line
+//     (8 independent probes in flight) and keeps the answers as two 128-bit planes + up to 8 parked
+//     (slot, skip distance) pairs;
+//   * phase 2: the walk of stitch2_walk.cuh -- find-first-set over scan_flags' bit planes and the K
+//     planes instead of a per-half-step loop.
+// Lines with more than S2_POS_CAP k-mer positions or more than 31 reservation slots are rare; the
+// warp that owns such a record processes it cooperatively with the code of stitch.cuh (direct path).
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "stitch.cuh"
+#include "stitch2_walk.cuh"
+
+namespace faucet {
+
+constexpr int S2_THREADS = 512;
+constexpr int S2_WARPS = S2_THREADS / 32;
+static_assert(S2_KEY_EMPTY == KEY_EMPTY, "one empty marker");
+
+// reservation rows: rows[32 r] = number of slots of record row_base + r (> 31: did not fit), then the slots
+__global__ void __launch_bounds__(256) stitch2_rows_kernel(StitchArgs a, uint32_t* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (gridDim.x * 256) >> 5;
+  for (uint32_t rec = a.row_base + gw; rec < a.row_end; rec += n_warps) {
+    const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
+    const uint32_t len = le > ls ? le - ls : 0u;
+    uint32_t* row = rows + (size_t)(rec - a.row_base) * S2_ROW;
+    int n = 0;
+    line_reservations<3, false>(a, a.packed, ls, len, rec, lane, row + 1, &n, S2_ROW - 1);
+    if (lane == 0) row[0] = (uint32_t)n;
+  }
+}
+
+struct DevEnv {
+  const StitchArgs& a;
+  int k, j, spacer;
+  bool pairs, want_ext;
+  unsigned st[S2_COUNTERS];
+  unsigned n_created;
+  unsigned long long stamp_next;
+  uint32_t rec, part, n_ext;
+  unsigned long long ext_buf[S2_EXT];
+
+  __device__ __forceinline__ uint32_t inval_word(uint32_t w) const { return __ldg(a.inval + w); }
+  __device__ __forceinline__ uint32_t fp_word(int p, uint32_t w) const { return __ldg(a.fplanes + (size_t)w * FP_STRIDE + p); }
+  __device__ __forceinline__ uint32_t packed_word(uint32_t w) const { return __ldg(a.packed + w); }
+  __device__ __forceinline__ uint64_t tbl_home(uint64_t key) const { return mix64(key) & (a.cap - 1); }
+  __device__ __forceinline__ uint64_t tbl_next(uint64_t h) const { return (h + 1) & (a.cap - 1); }
+  __device__ __forceinline__ uint64_t tbl_key(uint64_t h) const { return __ldcg(a.keys + h); }
+  __device__ __forceinline__ int find(uint64_t key) const { return tbl_find(a, key); }
+  __device__ __forceinline__ int insert(uint64_t key, bool* created) {
+    const int s = tbl_insert_nc(a, key, created);
+    if (*created) n_created++;
+    return s;
+  }
+  __device__ __forceinline__ void stamp(int slot) { a.stamps[slot] = stamp_next++; }
+  __device__ __forceinline__ uint32_t dist_peek(int slot, int idx) const { return __ldcg(rec_field(a, slot, REC_DIST + idx)); }
+  __device__ __forceinline__ void add_cov(int slot, int nt) const { rec_add_cov(a, slot, nt); }
+  __device__ __forceinline__ void update(int slot, int idx, int length) const { rec_update(a, slot, idx, length); }
+  __device__ __forceinline__ void link(int slot, int idx) const { rec_link(a, slot, idx); }
+  __device__ __forceinline__ uint32_t dist_now(int slot, int idx) const { return rec_dist_now(a, slot, idx); }
+  __device__ __forceinline__ void spf_pair(uint64_t k1, uint64_t k2) const { spf_add_pair(a, k1, k2); }
+  __device__ void ext_flush() {
+    // chunk = header {record:32 | part:16 | count:16} + count real-extension k-mers (pair_filter_host.hpp)
+    const unsigned long long off = atomicAdd(&a.st->ext_used, (unsigned long long)n_ext + 1);
+    a.ext[off] = ((unsigned long long)rec << 32) | ((unsigned long long)(part & 0xffffu) << 16) | n_ext;
+    for (uint32_t i = 0; i < n_ext; i++) a.ext[off + 1 + i] = ext_buf[i];
+    n_ext = 0;
+    part++;
+  }
+  __device__ __forceinline__ void ext_push(uint64_t kmer) {
+    ext_buf[n_ext++] = kmer;
+    if (n_ext == S2_EXT) ext_flush();
+  }
+};
+
+__global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char stitch_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratch* S = reinterpret_cast<WarpScratch*>(stitch_smem) + wib;  // direct path + per-warp counters
+  // window slot of this thread: consecutive warps of a window go to different SMs
+  const uint32_t my = (((uint32_t)wib * gridDim.x + blockIdx.x) << 5) + lane;
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  StitchState* st = a.st;
+  uint32_t next = __ldcg(&st->next), W = __ldcg(&st->W), round = __ldcg(&st->round);
+  if (W > a.w_max) W = a.w_max;
+  if (lane < SS_COUNT) S->st[lane] = 0;
+  __syncwarp();
+  WarpCtx c;
+  c.S = S; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0; c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0;
+  DevEnv e{a, a.k, a.j, a.spacer, !a.no_cleaning && a.spf != nullptr, a.ext != nullptr};
+  for (int i = 0; i < S2_COUNTERS; i++) e.st[i] = 0;
+  e.n_created = 0; e.n_ext = 0; e.part = 0; e.rec = 0; e.stamp_next = 0;
+  LineState L;
+  uint32_t status = ST_DONE;
+  unsigned long long need_seen = 0;  // the largest 2 len + 2 this thread has reported
+
+  while (true) {
+    const int cur = round & 1, nxt = cur ^ 1;
+    const uint32_t nd = __ldcg(&st->nd[cur]);
+    const uint32_t room = a.row_end - next;
+    const uint32_t n_new = W > nd ? (W - nd < room ? W - nd : room) : 0u;
+    const uint32_t n_win = nd + n_new;  // <= w_max <= threads of the grid
+    if (n_win == 0) {
+      if (a.row_end < a.n_recs) status = ST_MORE_ROWS;
+      break;
+    }
+    // n_entries / ext_used only move in phase 2, so this snapshot is the same in every thread
+    const unsigned long long entries0 = __ldcg(&st->n_entries), ext0 = __ldcg(&st->ext_used);
+    if (timer) __stcg(&st->nd[nxt], 0u);
+    // ---- phase 1: reservations + lookups of the thread's record
+    const unsigned long long t0 = gtime_ns();
+    const bool have = my < n_win;
+    uint32_t rec = 0, ls = 0, len = 0, n_res = 0;
+    int n_pos = 0;
+    bool simple = false;
+    const uint32_t* row = nullptr;
+    if (have) {
+      rec = my < nd ? __ldcg(a.deferred[cur] + my) : next + (my - nd);
+      ls = __ldg(a.seq_start + rec);
+      const uint32_t le = __ldg(a.seq_end + rec);
+      len = le > ls ? le - ls : 0u;
+      n_pos = len >= (uint32_t)a.k ? (int)(len - a.k + 1) : 0;
+      row = a.rows + (size_t)(rec - a.row_base) * S2_ROW;
+      n_res = __ldg(row);
+      simple = n_pos <= S2_POS_CAP && n_res < (uint32_t)S2_ROW;
+      if (simple) {
+        for (uint32_t i = 0; i < n_res; i++) atomicMin(a.res + __ldg(row + 1 + i), rec);
+        s2_lookup_line(e, L, ls, n_pos);
+      }
+      if (2ull * len + 2 > need_seen) {
+        need_seen = 2ull * len + 2;
+        if (need_seen > __ldcg(&st->max_need)) atomicMax(&st->max_need, need_seen);
+      }
+    }
+    const uint32_t hard_mask = __ballot_sync(0xffffffffu, have && !simple);
+    for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {  // rare: the warp reserves for these records together
+      const int src = __ffs(hm) - 1;
+      const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
+      int n_keep = 0;
+      line_reservations<0, false>(a, a.packed, ls_, len_, r_, lane, S->reskey, &n_keep);
+    }
+    const unsigned long long t1 = gtime_ns();
+    grid.sync();
+    const unsigned long long t2 = gtime_ns();
+    {
+      const unsigned long long bound = __ldcg(&st->max_need) * n_win;
+      if (entries0 + bound > (a.cap / 4) * 3) { status = ST_GROW_TABLE; break; }
+      if (a.ext && ext0 + 2 * bound + n_win > a.ext_cap) { status = ST_DRAIN_EXT; break; }
+    }
+    // ---- phase 2: execute or defer
+    bool mine = false;
+    if (have && simple) {
+      bool ok = true;
+      for (uint32_t i = 0; i < n_res; i++)
+        if (__ldcg(a.res + __ldg(row + 1 + i)) != rec) ok = false;
+      mine = ok;
+      for (uint32_t i = 0; i < n_res; i++) {
+        uint32_t* slot = a.res + __ldg(row + 1 + i);
+        if (__ldcg(slot) == rec) __stcg(slot, RES_FREE);
+      }
+    }
+    for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {
+      const int src = __ffs(hm) - 1;
+      const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
+      const bool m = line_reservations<1, false>(a, a.packed, ls_, len_, r_, lane, nullptr, nullptr);
+      line_reservations<2, false>(a, a.packed, ls_, len_, r_, lane, nullptr, nullptr);
+      if (lane == src) mine = m;
+    }
+    if (have && simple && mine) {
+      e.rec = rec; e.part = 0; e.n_ext = 0;
+      e.stamp_next = (a.rec_base + rec) << 20;
+      s2_line(e, L, ls, ls + len);
+      if (e.want_ext && e.n_ext) e.ext_flush();
+    }
+    for (uint32_t xm = __ballot_sync(0xffffffffu, have && !simple && mine); xm; xm &= xm - 1) {
+      const int src = __ffs(xm) - 1;
+      const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
+      c.rec = r_; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls_; c.n_pos = 0;
+      c.stamp = (a.rec_base + r_) << 20;
+      if (len_) scan_line<false>(a, c, ls_, ls_ + len_, lane);
+      if (a.ext && c.n_stage) ext_flush(a, c, lane);
+    }
+    {  // deferred records go to the next round's list (one atomic per warp)
+      const uint32_t dm = __ballot_sync(0xffffffffu, have && !mine);
+      if (dm) {
+        uint32_t base = 0;
+        if (lane == 0) { base = atomicAdd(&st->nd[nxt], (uint32_t)__popc(dm)); S->st[SS_DEFERRED] += (unsigned)__popc(dm); }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (have && !mine) a.deferred[nxt][base + __popc(dm & ((1u << lane) - 1u))] = rec;
+      }
+      unsigned nc = __reduce_add_sync(0xffffffffu, e.n_created);
+      e.n_created = 0;
+      if (lane == 0 && nc) atomicAdd(&st->n_entries, (unsigned long long)nc);
+    }
+    const unsigned long long t3 = gtime_ns();
+    grid.sync();
+    if (timer) {
+      S->st[SS_T_PHASE1] += t1 - t0; S->st[SS_T_SYNC1] += t2 - t1; S->st[SS_T_PHASE2] += t3 - t2; S->st[SS_T_SYNC2] += gtime_ns() - t3;
+      S->st[SS_ROUNDS]++;
+    }
+    const uint32_t nd_next = __ldcg(&st->nd[nxt]);
+    if (nd_next >= n_win) { status = ST_STUCK; break; }  // cannot happen: the earliest record of a window always executes
+    if (nd_next * a.shrink_den > n_win) W = W / 2 > a.w_min ? W / 2 : a.w_min;
+    else if (nd_next * a.grow_den < n_win && n_win >= W) W = W * 2 < a.w_max ? W * 2 : a.w_max;
+    next += n_new;
+    round++;
+  }
+  // counters: thread path (registers) + direct path / scheduling (shared) -> device state
+  {
+    const int map[S2_COUNTERS] = {SS_JCHECK, SS_NOJUNC, SS_PROCESSED, SS_SKIPPED, SS_NOERR, SS_UNAMBIG};
+#pragma unroll
+    for (int i = 0; i < S2_COUNTERS; i++) {
+      // 32-bit per-thread counters, 64-bit sum
+      unsigned long long v = e.st[i];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) S->st[map[i]] += v;
+    }
+  }
+  __syncwarp();
+  if (lane < SS_COUNT && S->st[lane]) atomicAdd(&st->stats[lane], S->st[lane]);
+  if (timer) {
+    __stcg(&st->next, next); __stcg(&st->W, W); __stcg(&st->round, round); __stcg(&st->status, status);
+  }
+}
+
+}  // namespace faucet

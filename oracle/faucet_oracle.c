@@ -447,7 +447,8 @@ static uint64_t add_fake_junction(scanner_t* s, const char* read, int len) {
   cursor_t m;
   cur_init(&m, read, len, s->k, len / 2 - s->k / 2, 1);
   uint64_t ext = cur_real_extension(&m);
-  fo_junction_rec* r = &s->map.recs[jmap_create(&s->map, cur_kmer(&m))];
+  const int64_t ji = jmap_create(&s->map, cur_kmer(&m)); /* may realloc map.recs: index first, pointer after */
+  fo_junction_rec* r = &s->map.recs[ji];
   junc_add_cov(r, cur_real_nuc(&m));
   junc_update(r, cur_ext_index(&m, 0), cur_total_pos(&m) - 2 * s->j);
   junc_update(r, cur_ext_index(&m, 1), cur_dist_to_end(&m) - 2 * s->j);

@@ -42,6 +42,14 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
+@pytest.fixture(params=[2, 1], ids=["thread_per_record", "warp_per_record"])
+def impl(request, fb):
+    """both stitch kernels (faucet_b200/csrc/stitch2.cuh, the default, and stitch.cuh) are held to the same bar"""
+    fb.set_tuning("stitch_impl", request.param)
+    yield request.param
+    fb.set_tuning("stitch_impl", 2)
+
+
 def _geom(oracle, est, sing, fp=0.04):
     p1 = ctypes.c_float(oracle.lib.fo_brent_p1(est, sing, fp)).value
     return oracle.geometry_optimal(est, p1)
@@ -92,7 +100,7 @@ def test_load_multibatch_and_epochs(fb, oracle, small_fq):
 
 @pytest.mark.parametrize("j", [0, 1, 2])
 @pytest.mark.parametrize("no_cleaning", [1, 0])
-def test_scan_matches_oracle(fb, oracle, small_fq, j, no_cleaning):
+def test_scan_matches_oracle(fb, oracle, small_fq, j, no_cleaning, impl):
     _, text = small_fq
     k = 31
     lt, nh = _geom(oracle, 100000, 50000)
@@ -108,7 +116,7 @@ def test_scan_matches_oracle(fb, oracle, small_fq, j, no_cleaning):
     assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
 
 
-def test_scan_fasta_spacers_multibatch(fb, oracle, small_fa):
+def test_scan_fasta_spacers_multibatch(fb, oracle, small_fa, impl):
     """150 bp reads with max_spacer_dist 40 (spacers fire), FASTA, unpaired, tiny batches"""
     _, text = small_fa
     k = 25
@@ -126,7 +134,7 @@ def test_scan_fasta_spacers_multibatch(fb, oracle, small_fa):
 
 @pytest.mark.parametrize("tail", [b"", b"\n", b"@last", b"@lastACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT",
                                   b"@h\nACGTNACG", b"@h\nACGTACGTACGTAGCTAGCTAGCTAGCATCGATCGATCAGCTAGC\n+", b"\n\n"])
-def test_ragged_tails(fb, oracle, small_fq, tail):
+def test_ragged_tails(fb, oracle, small_fq, tail, impl):
     """truncated / unterminated inputs, including the header-reused-as-sequence getline quirk"""
     _, text = small_fq
     text = text[:40_000]
@@ -141,7 +149,7 @@ def test_ragged_tails(fb, oracle, small_fq, tail):
     assert gsst == osst and _strip(grecs) == _strip(orecs)
 
 
-def test_empty_and_tiny_inputs(fb, oracle):
+def test_empty_and_tiny_inputs(fb, oracle, impl):
     k, lt, nh = 31, 16, 4
     for text in (b"", b"\n", b">x\n", b">x\nACGT\n", b">x\n" + b"ACGT" * 8 + b"\n",
                  b">x\n" + b"ACGT" * 7 + b"ACG" + b"\n", b">x\r\n" + b"ACGT" * 10 + b"\r\n"):
@@ -182,8 +190,10 @@ def test_session_stage_api(fb, oracle, small_fq):
     {"stitch_w0": 1, "stitch_w_max": 1},                  # one record per round == plain sequential order
     {"stitch_w0": 32768, "stitch_w_max": 32768},          # window far larger than the genome supports
     {"table_cap0": 256, "ext_cap0": 256, "res_log2": 10, "stitch_w0": 512},
+    {"rows_max": 100, "stitch_w0": 64},                   # thread-per-record kernel: reservation rows listed 100 records at a time
+    {"stitch_w0": 1 << 17, "stitch_w_max": 1 << 17},      # more window than the warp-per-record grid has warps
 ])
-def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs):
+def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs, impl):
     """whatever the round schedule of the GPU stitch (window, collisions, growth, drains), the junction
     map, counters and pair filters equal the sequential oracle's"""
     _, text = small_fq
@@ -194,7 +204,8 @@ def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs):
     ospf, olpf = np.zeros((1 << sg[0]) // 8, np.uint8), np.zeros((1 << lg[0]) // 8, np.uint8)
     gspf, glpf = ospf.copy(), olpf.copy()
     orecs, ost = oracle.scan(text, True, True, 0, k, j, 100, b2, lt, nh, ospf, sg, olpf, lg)
-    defaults = {"table_cap0": 1 << 22, "ext_cap0": 1 << 24, "res_log2": 24, "stitch_w0": 2048, "stitch_w_max": 1 << 15}
+    defaults = {"table_cap0": 1 << 22, "ext_cap0": 1 << 24, "res_log2": 24, "stitch_w0": 2048, "stitch_w_max": 1 << 15,
+                "rows_max": 1 << 22}
     try:
         for name, v in knobs.items():
             fb.set_tuning(name, v)
@@ -211,7 +222,7 @@ def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs):
     assert tim["stitch_rounds"] > 0
 
 
-def test_stitch_repetitive_reads(fb, oracle, tmp_path_factory):
+def test_stitch_repetitive_reads(fb, oracle, tmp_path_factory, impl):
     """every read drawn from a 2 kbp genome at 400x: nearly all records conflict with their neighbours"""
     p, text = _dataset(tmp_path_factory, "rep.fq", genome=2000, cov=400, length=100, insert=300, seed=17, err=0.01)
     k, lt, nh = 21, 18, 3
@@ -222,7 +233,31 @@ def test_stitch_repetitive_reads(fb, oracle, tmp_path_factory):
         assert gst == ost and _strip(grecs) == _strip(orecs)
 
 
-def test_scan_k32_all_g_key(fb, oracle):
+def test_stitch_mixed_line_lengths(fb, oracle, tmp_path_factory, impl):
+    """100 bp and 300 bp reads of one genome interleaved file-wise: the long lines (280 k-mer positions, more
+    reservation slots than a row holds) take the warp-cooperative path inside the thread-per-record kernel"""
+    _, short = _dataset(tmp_path_factory, "mix_s.fq", genome=30000, cov=15, length=100, insert=300, seed=21, err=0.005, nrate=0.002)
+    _, long_ = _dataset(tmp_path_factory, "mix_l.fq", genome=30000, cov=15, length=300, insert=700, seed=21, err=0.005, nrate=0.002)
+    a, b = short.split(b"\n")[:-1], long_.split(b"\n")[:-1]
+    recs = []
+    for i in range(0, max(len(a), len(b)), 8):  # two mate pairs of one file, then two of the other
+        recs += a[i:i + 8] + b[i:i + 8]
+    text = b"\n".join(recs) + b"\n"
+    k, j, lt, nh = 21, 1, 20, 3
+    o1, o2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    g2, _, _ = fb.load_two_filters_mem(text, True, k, lt, nh)
+    assert np.array_equal(g2, o2)
+    sg, lg = oracle.geometry_optimal(3000, 0.01), oracle.geometry_optimal(6000, 0.01)
+    for no_cleaning in (1, 0):
+        ospf, olpf = np.zeros((1 << sg[0]) // 8, np.uint8), np.zeros((1 << lg[0]) // 8, np.uint8)
+        gspf, glpf = ospf.copy(), olpf.copy()
+        orecs, ost = oracle.scan(text, True, True, no_cleaning, k, j, 60, o2, lt, nh, ospf, sg, olpf, lg)
+        grecs, gst = fb.scan_mem(text, True, True, no_cleaning, k, j, 60, o2, lt, nh, gspf, sg, glpf, lg)
+        assert gst == ost and _strip(grecs) == _strip(orecs)
+        assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
+
+
+def test_scan_k32_all_g_key(fb, oracle, impl):
     """k = 32: the all-'G' k-mer has the bit pattern of the table's empty marker"""
     reads = [b"G" * 70, b"ACGT" * 5 + b"G" * 40 + b"TTGCA" * 4, b"C" * 70, b"G" * 50 + b"A" + b"G" * 40]
     text = b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(reads * 3))

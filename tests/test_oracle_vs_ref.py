@@ -105,3 +105,22 @@ def test_fake_bloom_vectors_agree(oracle, ref):
         assert np.array_equal(sort_recs(orecs), sort_recs(rrecs)), name
         for f in ("nb_jcheck_kmer", "nb_no_juncs", "nb_processed", "nb_skipped", "reads_no_errors", "unambiguous_reads"):
             assert ost[f] == rst[f], (name, f)
+
+
+def test_fake_junction_that_grows_the_map(oracle, ref, tmp_path):
+    """regression: the junction that fills the oracle's record array (the 1025th here) is a mid-read FAKE
+    junction; the oracle once took the record pointer before the creation reallocated the array and lost
+    that junction's coverage / distances.  Found by tests/test_stitch2_host.py; pinned here."""
+    kw = dict(genome=60000, cov=30, length=100, insert=300, seed=3, err=0.005, nrate=0.002, repeats=True)
+    full = open(gen_reads(str(tmp_path / "full.fq"), **kw), "rb").read()
+    text = b"\n".join(full.split(b"\n")[:4 * 2568]) + b"\n"
+    path = str(tmp_path / "trunc.fq")
+    open(path, "wb").write(text)
+    k, j = 31, 1
+    lt, nh = oracle.geometry_optimal(120000, 0.04)
+    _, b2, _ = oracle.load_two_filters(full, True, k, lt, nh)
+    rrecs, rst = ref.scan(path, True, True, 1, k, j, 100, b2, lt, nh)
+    orecs, ost = oracle.scan(text, True, True, 1, k, j, 100, b2, lt, nh)
+    assert len(orecs) == 1025 and ost == rst
+    assert np.array_equal(sort_recs(orecs), sort_recs(rrecs))
+    assert orecs[-1]["cov"].sum() == 1  # the fake junction kept its coverage
