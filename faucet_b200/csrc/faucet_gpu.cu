@@ -33,7 +33,7 @@ struct Global {
   int res_log2 = 24;                           // reservation table entries (u32 each)
   uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048, stitch_shrink_den = 4, stitch_grow_den = 10;
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
-  int stitch_impl = 2;    // 2: one thread per record (stitch2.cuh); 1: one warp per record (stitch.cuh)
+  int stitch_impl = 1;    // 1: one warp per record (stitch.cuh, the faster one as measured); 2: one thread walks a record (stitch2.cuh)
   size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
   unsigned long long ext_cap0 = 1ull << 24;
   size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
@@ -618,7 +618,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   s->w_max = g.stitch_w_max;
   if (!s->stitch_grid && s->impl == 2) {
     int per_sm = 0;
-    const size_t smem = S2_WARPS * sizeof(WarpScratch);
+    const size_t smem = S2_SMEM;
     s->stitch_fn = (const void*)stitch2_kernel;
     CU(cudaFuncSetAttribute(s->stitch_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->stitch_fn, S2_THREADS, smem));
@@ -639,7 +639,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     s->stitch_grid = per_sm * g.sm_count;
   }
   // one record per warp (thread) per round
-  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * (s->impl == 2 ? S2_THREADS : STITCH_WARPS));
+  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * (s->impl == 2 ? S2_WARPS * S2_RPW : STITCH_WARPS));
   if (!s->d_res) {
     if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
@@ -724,8 +724,7 @@ int faucet_session_stitch_batch(faucet_session* s) {
           s->launches++;
           rows_ready = true;
         }
-        CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(S2_THREADS), params,
-                                       S2_WARPS * sizeof(WarpScratch), s->stream));
+        CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(S2_THREADS), params, S2_SMEM, s->stream));
       } else {
         CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(STITCH_THREADS), params,
                                        STITCH_WARPS * sizeof(WarpScratch), s->stream));

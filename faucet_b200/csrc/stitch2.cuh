@@ -1,21 +1,27 @@
-// Pass 2, stream-order part: ONE THREAD per record (the default stitch; stitch.cuh keeps the
-// warp-per-record kernel it grew out of, selectable with faucet_gpu_set_tuning("stitch_impl", 1)).
+// Pass 2, stream-order part, second kernel: ONE THREAD walks a record (stitch.cuh holds the default
+// warp-per-record kernel; this one is selected with faucet_gpu_set_tuning("stitch_impl", 2)).
 //
 // Same schedule as stitch.cuh -- windowed deterministic reservations on minimizers, two grid barriers
-// per round, junction table in HBM -- but the per-round parallelism of that kernel was capped by "one
-// record per warp": 3.5 k records per round on a B200 while the E. coli-sized workload supports ~9 k
-// conflict-free records per round (window ~14-28 k).  Here a record is one thread:
+// per round, junction table in HBM.  The per-round parallelism of that kernel is capped by "one record
+// per warp" (3.5 k records per round on a B200, while the E. coli-sized workload supports ~8 k
+// conflict-free records per round at a window of ~14 k).  Here a warp holds 1..16 records per round:
 //   * the minimizer reservation slots of every record are a pure function of the text and are listed
-//     once per batch by stitch2_rows_kernel (one 128-byte row per record), so reserving / checking /
-//     releasing is 1-2 vector loads and <= 31 atomics per thread and no minimizer is computed inside
-//     the round loop;
-//   * phase 1: the thread looks up the FORWARD and BACKWARD key of every k-mer position of its line
-//     (8 independent probes in flight) and keeps the answers as two 128-bit planes + up to 8 parked
-//     (slot, skip distance) pairs;
-//   * phase 2: the walk of stitch2_walk.cuh -- find-first-set over scan_flags' bit planes and the K
-//     planes instead of a per-half-step loop.
+//     once per batch by stitch2_rows_kernel (one 128-byte row per record): reserving is <= 31 atomics
+//     and checking + releasing is one trip, with no minimizer computed inside the round loop;
+//   * phase 1: the G = 32, 16, .. 2 lanes that share a record stage the line's plane words in shared
+//     memory and look up the FORWARD and BACKWARD key of every k-mer position; the answers are two
+//     128-bit K planes + up to 8 parked (slot, skip distance) pairs in the record's shared-memory slot;
+//   * phase 2: one thread per record runs the walk of stitch2_walk.cuh -- find-first-set over
+//     scan_flags' bit planes and the K planes instead of a per-half-step loop.
 // Lines with more than S2_POS_CAP k-mer positions or more than 31 reservation slots are rare; the
 // warp that owns such a record processes it cooperatively with the code of stitch.cuh (direct path).
+//
+// Measured (B200, 4.6 Mbp x 100x x 150 bp, profiles/r1_stitch2_sweep.txt): bit-exact like stitch.cuh, but
+// 53-59 ms against 35.5 ms.  The single-thread walk is ~2.6 k dependent instructions (8.5 us, with a 19 us
+// tail behind the second barrier: s2_publish after a creation is a serial scan of the line), and with
+// G < 16 lanes per record the lookups of phase 1 stretch faster than the window adds parallelism
+// (16 us at G = 16, 40 us at G = 4).  Kept as a tested alternative and as the device half of the
+// host-compiled walk that tests/test_stitch2_host.py holds to the oracle.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -44,6 +50,20 @@ __global__ void __launch_bounds__(256) stitch2_rows_kernel(StitchArgs a, uint32_
   }
 }
 
+// the line's words of every plane, staged in shared memory by the lanes that share the record
+struct LineStage {
+  uint32_t fp[6 * FP_STRIDE];  // flag planes, from word ls >> 5 (a line of <= 159 bytes spans <= 6 words)
+  uint32_t inv[6];             // validity plane, from word ls >> 5
+  uint32_t pk[13];             // 2-bit plane, from word ls >> 4 (11 words + the 2 a k-mer fetch may run over)
+  uint32_t pad;
+};
+struct RecSlot {
+  LineStage G;
+  LineState L;
+};
+constexpr int S2_RPW = 16;  // records one warp may hold per round (2 lanes each); fewer records => more lanes per record
+constexpr size_t S2_SMEM = (size_t)S2_WARPS * (sizeof(WarpScratch) + S2_RPW * sizeof(RecSlot));
+
 struct DevEnv {
   const StitchArgs& a;
   int k, j, spacer;
@@ -52,11 +72,13 @@ struct DevEnv {
   unsigned n_created;
   unsigned long long stamp_next;
   uint32_t rec, part, n_ext;
+  const LineStage* G;
+  uint32_t w5, w4;  // ls >> 5, ls >> 4: word 0 of the staged planes
   unsigned long long ext_buf[S2_EXT];
 
-  __device__ __forceinline__ uint32_t inval_word(uint32_t w) const { return __ldg(a.inval + w); }
-  __device__ __forceinline__ uint32_t fp_word(int p, uint32_t w) const { return __ldg(a.fplanes + (size_t)w * FP_STRIDE + p); }
-  __device__ __forceinline__ uint32_t packed_word(uint32_t w) const { return __ldg(a.packed + w); }
+  __device__ __forceinline__ uint32_t inval_word(uint32_t w) const { return G->inv[w - w5]; }
+  __device__ __forceinline__ uint32_t fp_word(int p, uint32_t w) const { return G->fp[(w - w5) * FP_STRIDE + p]; }
+  __device__ __forceinline__ uint32_t packed_word(uint32_t w) const { return G->pk[w - w4]; }
   __device__ __forceinline__ uint64_t tbl_home(uint64_t key) const { return mix64(key) & (a.cap - 1); }
   __device__ __forceinline__ uint64_t tbl_next(uint64_t h) const { return (h + 1) & (a.cap - 1); }
   __device__ __forceinline__ uint64_t tbl_key(uint64_t h) const { return __ldcg(a.keys + h); }
@@ -87,13 +109,59 @@ struct DevEnv {
   }
 };
 
+// phase 1, cooperative: the G lanes that share a record look up both keys of every k-mer position
+// (positions strided over the lanes, two positions = four probes in flight per lane) and leave the
+// answers in the record's shared-memory slot: K planes by atomicOr, the first S2_PARK hits parked.
+__device__ __forceinline__ void s2_lookup_group(const StitchArgs& a, RecSlot& RS, uint32_t ls, int n_pos, int lgi, int G) {
+  const int k = a.k;
+  const uint32_t o4 = ls & 15u;
+  for (int p0 = lgi; p0 < n_pos; p0 += 2 * G) {
+    uint64_t kk[4], hh[4], got[4];
+    int pos[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      pos[u] = p0 + u * G;
+      const uint64_t f = kmer_at_t<true>(RS.G.pk, o4 + (pos[u] < n_pos ? pos[u] : 0), k);
+      kk[2 * u] = f; kk[2 * u + 1] = revcomp(f, k);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      hh[v] = mix64(kk[v]) & (a.cap - 1);
+      got[v] = __ldcg(a.keys + hh[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int ps = pos[v >> 1];
+      if (ps >= n_pos) continue;
+      const int dir = (v & 1) ? 0 : 1;  // even entries hold the forward k-mer = the FORWARD key
+      int slot = -1;
+      if (kk[v] == KEY_EMPTY) slot = tbl_find(a, kk[v]);
+      else {
+        while (got[v] != kk[v] && got[v] != KEY_EMPTY) { hh[v] = (hh[v] + 1) & (a.cap - 1); got[v] = __ldcg(a.keys + hh[v]); }
+        if (got[v] == kk[v]) slot = (int)hh[v];
+      }
+      if (slot < 0) continue;
+      atomicOr((dir ? RS.L.kf : RS.L.kb) + (ps >> 5), 1u << (ps & 31));
+      const uint32_t at = atomicAdd(&RS.L.n_park, 1u);
+      if (at < (uint32_t)S2_PARK) {
+        // dist[fwdIdx]: facing forward fwdIdx = the read's next base, facing backward fwdIdx = 4
+        const int idx = dir ? (int)code_at_t<true>(RS.G.pk, o4 + ps + k) : 4;
+        RS.L.pslot[at] = (uint32_t)slot;
+        RS.L.pinfo[at] = ((uint32_t)(2 * ps + dir) << 8) | (__ldcg(rec_field(a, slot, REC_DIST + idx)) & 0xffu);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char stitch_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpScratch* S = reinterpret_cast<WarpScratch*>(stitch_smem) + wib;  // direct path + per-warp counters
-  // window slot of this thread: consecutive warps of a window go to different SMs
-  const uint32_t my = (((uint32_t)wib * gridDim.x + blockIdx.x) << 5) + lane;
+  RecSlot* slots = reinterpret_cast<RecSlot*>(stitch_smem + S2_WARPS * sizeof(WarpScratch)) + wib * S2_RPW;
+  // consecutive window slots go to different SMs: slot i belongs to warp i mod (warps of the grid)
+  const uint32_t total_warps = gridDim.x * S2_WARPS;
+  const uint32_t gw = (uint32_t)wib * gridDim.x + blockIdx.x;
   const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
   StitchState* st = a.st;
   uint32_t next = __ldcg(&st->next), W = __ldcg(&st->W), round = __ldcg(&st->round);
@@ -104,8 +172,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
   c.S = S; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0; c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0;
   DevEnv e{a, a.k, a.j, a.spacer, !a.no_cleaning && a.spf != nullptr, a.ext != nullptr};
   for (int i = 0; i < S2_COUNTERS; i++) e.st[i] = 0;
-  e.n_created = 0; e.n_ext = 0; e.part = 0; e.rec = 0; e.stamp_next = 0;
-  LineState L;
+  e.n_created = 0; e.n_ext = 0; e.part = 0; e.rec = 0; e.stamp_next = 0; e.G = nullptr; e.w5 = 0; e.w4 = 0;
   uint32_t status = ST_DONE;
   unsigned long long need_seen = 0;  // the largest 2 len + 2 this thread has reported
 
@@ -114,7 +181,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
     const uint32_t nd = __ldcg(&st->nd[cur]);
     const uint32_t room = a.row_end - next;
     const uint32_t n_new = W > nd ? (W - nd < room ? W - nd : room) : 0u;
-    const uint32_t n_win = nd + n_new;  // <= w_max <= threads of the grid
+    const uint32_t n_win = nd + n_new;  // <= w_max <= S2_RPW * warps of the grid
     if (n_win == 0) {
       if (a.row_end < a.n_recs) status = ST_MORE_ROWS;
       break;
@@ -122,7 +189,15 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
     // n_entries / ext_used only move in phase 2, so this snapshot is the same in every thread
     const unsigned long long entries0 = __ldcg(&st->n_entries), ext0 = __ldcg(&st->ext_used);
     if (timer) __stcg(&st->nd[nxt], 0u);
-    // ---- phase 1: reservations + lookups of the thread's record
+    // records per warp this round (a power of two) and lanes per record
+    int lg2 = 0;
+    while (((uint64_t)total_warps << lg2) < n_win) lg2++;
+    const int G = 32 >> lg2;
+    const int gid = lane >> (5 - lg2), lgi = lane & (G - 1);
+    const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (gid * G));
+    const uint32_t my = gw + total_warps * (uint32_t)gid;
+    RecSlot& RS = slots[gid];
+    // ---- phase 1: reservations + lookups of the group's record
     const unsigned long long t0 = gtime_ns();
     const bool have = my < n_win;
     uint32_t rec = 0, ls = 0, len = 0, n_res = 0;
@@ -139,15 +214,21 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       n_res = __ldg(row);
       simple = n_pos <= S2_POS_CAP && n_res < (uint32_t)S2_ROW;
       if (simple) {
-        for (uint32_t i = 0; i < n_res; i++) atomicMin(a.res + __ldg(row + 1 + i), rec);
-        s2_lookup_line(e, L, ls, n_pos);
+        for (uint32_t i = lgi; i < n_res; i += G) atomicMin(a.res + __ldg(row + 1 + i), rec);
+        const uint32_t* fp = a.fplanes + (size_t)(ls >> 5) * FP_STRIDE;
+        for (int i = lgi; i < 6 * FP_STRIDE; i += G) RS.G.fp[i] = __ldg(fp + i);
+        for (int i = lgi; i < 6; i += G) RS.G.inv[i] = __ldg(a.inval + (ls >> 5) + i);
+        for (int i = lgi; i < 13; i += G) RS.G.pk[i] = __ldg(a.packed + (ls >> 4) + i);
+        for (int i = lgi; i < (int)(sizeof(LineState) / 4); i += G) reinterpret_cast<uint32_t*>(&RS.L)[i] = 0u;
       }
-      if (2ull * len + 2 > need_seen) {
+      if (lgi == 0 && 2ull * len + 2 > need_seen) {
         need_seen = 2ull * len + 2;
         if (need_seen > __ldcg(&st->max_need)) atomicMax(&st->max_need, need_seen);
       }
     }
-    const uint32_t hard_mask = __ballot_sync(0xffffffffu, have && !simple);
+    __syncwarp();
+    if (have && simple) s2_lookup_group(a, RS, ls, n_pos, lgi, G);
+    const uint32_t hard_mask = __ballot_sync(0xffffffffu, have && !simple && lgi == 0);
     for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {  // rare: the warp reserves for these records together
       const int src = __ffs(hm) - 1;
       const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
@@ -163,17 +244,15 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       if (a.ext && ext0 + 2 * bound + n_win > a.ext_cap) { status = ST_DRAIN_EXT; break; }
     }
     // ---- phase 2: execute or defer
-    bool mine = false;
-    if (have && simple) {
-      bool ok = true;
-      for (uint32_t i = 0; i < n_res; i++)
-        if (__ldcg(a.res + __ldg(row + 1 + i)) != rec) ok = false;
-      mine = ok;
-      for (uint32_t i = 0; i < n_res; i++) {
+    bool bad = false;
+    if (have && simple)
+      for (uint32_t i = lgi; i < n_res; i += G) {  // check and release in one trip
         uint32_t* slot = a.res + __ldg(row + 1 + i);
-        if (__ldcg(slot) == rec) __stcg(slot, RES_FREE);
+        if (__ldcg(slot) != rec) bad = true;
+        else __stcg(slot, RES_FREE);
       }
-    }
+    const uint32_t badm = __ballot_sync(0xffffffffu, bad);
+    bool mine = have && simple && !(badm & gmask);  // meaningful in the group's first lane
     for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {
       const int src = __ffs(hm) - 1;
       const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
@@ -181,13 +260,15 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       line_reservations<2, false>(a, a.packed, ls_, len_, r_, lane, nullptr, nullptr);
       if (lane == src) mine = m;
     }
-    if (have && simple && mine) {
+    const unsigned long long t2b = gtime_ns();
+    if (have && simple && mine && lgi == 0) {  // one thread walks the line out of shared memory
       e.rec = rec; e.part = 0; e.n_ext = 0;
       e.stamp_next = (a.rec_base + rec) << 20;
-      s2_line(e, L, ls, ls + len);
+      e.G = &RS.G; e.w5 = ls >> 5; e.w4 = ls >> 4;
+      s2_line(e, RS.L, ls, ls + len);
       if (e.want_ext && e.n_ext) e.ext_flush();
     }
-    for (uint32_t xm = __ballot_sync(0xffffffffu, have && !simple && mine); xm; xm &= xm - 1) {
+    for (uint32_t xm = __ballot_sync(0xffffffffu, have && !simple && mine && lgi == 0); xm; xm &= xm - 1) {
       const int src = __ffs(xm) - 1;
       const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
       c.rec = r_; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls_; c.n_pos = 0;
@@ -196,17 +277,19 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       if (a.ext && c.n_stage) ext_flush(a, c, lane);
     }
     {  // deferred records go to the next round's list (one atomic per warp)
-      const uint32_t dm = __ballot_sync(0xffffffffu, have && !mine);
+      const bool defer = have && !mine && lgi == 0;
+      const uint32_t dm = __ballot_sync(0xffffffffu, defer);
       if (dm) {
         uint32_t base = 0;
         if (lane == 0) { base = atomicAdd(&st->nd[nxt], (uint32_t)__popc(dm)); S->st[SS_DEFERRED] += (unsigned)__popc(dm); }
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (have && !mine) a.deferred[nxt][base + __popc(dm & ((1u << lane) - 1u))] = rec;
+        if (defer) a.deferred[nxt][base + __popc(dm & ((1u << lane) - 1u))] = rec;
       }
       unsigned nc = __reduce_add_sync(0xffffffffu, e.n_created);
       e.n_created = 0;
       if (lane == 0 && nc) atomicAdd(&st->n_entries, (unsigned long long)nc);
     }
+    if (timer) { S->st[SS_T_P1A] += t2b - t2; }
     const unsigned long long t3 = gtime_ns();
     grid.sync();
     if (timer) {

@@ -58,11 +58,11 @@ FHD int s2_clz(uint32_t x) {  // x != 0
 struct LineState {
   uint32_t kf[S2_KW], kb[S2_KW];  // K planes: bit r <=> the FORWARD / BACKWARD key at position ls + r is a junction
   uint32_t pslot[S2_PARK];        // parked: table slot ...
-  uint16_t pt[S2_PARK];           // ... of the key at line half-step 2 r + dir
-  uint8_t phop[S2_PARK];          // ... and its dist[fwdIdx] when the round started
-  uint8_t pstale;                 // bit i: the line has touched that junction since (phop[i] may be stale)
-  uint8_t n_park;
+  uint32_t pinfo[S2_PARK];        // ... of the key at line half-step t = 2 r + dir, and its dist[fwdIdx] when the round started: t << 8 | dist
+  uint32_t n_park;                // hits seen (only the first S2_PARK are parked)
+  uint32_t pstale;                // bit i: the line has touched that junction since (the parked distance may be stale)
 };
+FHD int s2_parked(const LineState& L) { return L.n_park < (uint32_t)S2_PARK ? (int)L.n_park : S2_PARK; }
 
 // ---- bit-plane views ------------------------------------------------------------------------------
 template <class E, int P>
@@ -186,14 +186,13 @@ FHD void s2_lookup_line(const E& e, LineState& L, uint32_t ls, int n_pos) {
       }
       if (slot < 0) continue;
       (dir ? L.kf : L.kb)[pos >> 5] |= 1u << (pos & 31);
-      if (L.n_park < S2_PARK) {
+      if (L.n_park < (uint32_t)S2_PARK) {
         // dist[fwdIdx]: facing forward fwdIdx = the read's next base, facing backward fwdIdx = 4 (utils/ReadKmer.cpp:95-100)
         const int idx = dir ? (int)s2_code_at(e, ls + pos + k) : 4;
         L.pslot[L.n_park] = (uint32_t)slot;
-        L.pt[L.n_park] = (uint16_t)(2 * pos + dir);
-        L.phop[L.n_park] = (uint8_t)e.dist_peek((int)slot, idx);
-        L.n_park++;
+        L.pinfo[L.n_park] = ((uint32_t)(2 * pos + dir) << 8) | (e.dist_peek((int)slot, idx) & 0xffu);
       }
+      L.n_park++;
     }
   }
 }
@@ -245,8 +244,8 @@ FHD void s2_subread(E& e, LineState& L, uint32_t ls, int n_pos, uint32_t s0, int
     if (e.want_ext) e.ext_push(real_ext);
   };
   auto touch = [&](int slot) {  // whatever was parked about this junction may be stale from now on
-    for (int i = 0; i < L.n_park; i++)
-      if (L.pslot[i] == (uint32_t)slot) L.pstale |= (uint8_t)(1u << i);
+    for (int i = 0; i < s2_parked(L); i++)
+      if (L.pslot[i] == (uint32_t)slot) L.pstale |= 1u << i;
   };
 
   while (tp < tested_end) {
@@ -293,11 +292,11 @@ FHD void s2_subread(E& e, LineState& L, uint32_t ls, int n_pos, uint32_t s0, int
     int slot = -1, hop = -1;
     bool created = false;
     if (known) {
-      const int tl = 2 * (rel0 + pos) + dir;
-      for (int i = 0; i < L.n_park; i++)
-        if (L.pt[i] == (uint16_t)tl) {
+      const uint32_t tl = (uint32_t)(2 * (rel0 + pos) + dir);
+      for (int i = 0; i < s2_parked(L); i++)
+        if ((L.pinfo[i] >> 8) == tl) {
           slot = (int)L.pslot[i];
-          if (!((L.pstale >> i) & 1u)) hop = L.phop[i];
+          if (!((L.pstale >> i) & 1u)) hop = (int)(L.pinfo[i] & 0xffu);
           break;
         }
       if (slot < 0) slot = e.find(key);  // beyond the parking space, or published by this line

@@ -42,12 +42,12 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
-@pytest.fixture(params=[2, 1], ids=["thread_per_record", "warp_per_record"])
+@pytest.fixture(params=[1, 2], ids=["warp_per_record", "thread_walks_record"])
 def impl(request, fb):
-    """both stitch kernels (faucet_b200/csrc/stitch2.cuh, the default, and stitch.cuh) are held to the same bar"""
+    """both stitch kernels (faucet_b200/csrc/stitch.cuh, the default, and stitch2.cuh) are held to the same bar"""
     fb.set_tuning("stitch_impl", request.param)
     yield request.param
-    fb.set_tuning("stitch_impl", 2)
+    fb.set_tuning("stitch_impl", 1)
 
 
 def _geom(oracle, est, sing, fp=0.04):

@@ -25,7 +25,8 @@ n = raw.size
 CONFIGS = [dict(), dict(stitch_blocks=3), dict(stitch_shrink_den=2, stitch_grow_den=4), dict(stitch_w_max=1024)]
 if os.environ.get("SWEEP"):
     CONFIGS = [json.loads(x) for x in os.environ["SWEEP"].split(";")]
-DEFAULT = dict(stitch_blocks=3, stitch_shrink_den=4, stitch_grow_den=10, stitch_w_max=1 << 15)
+DEFAULT = dict(stitch_impl=1, stitch_blocks=3, stitch_shrink_den=4, stitch_grow_den=10, stitch_w_max=1 << 15, res_log2=24,
+               table_cap0=1 << 22)
 ref = None
 for cfg in CONFIGS:
     for kk, v in {**DEFAULT, **cfg}.items():
