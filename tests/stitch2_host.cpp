@@ -118,6 +118,7 @@ struct HostEnv {
   std::vector<uint64_t> ext;
   uint32_t rec = 0, part = 0;
   std::vector<uint64_t> ext_buf;
+  bool changed = false;  // the current record created a junction or raised a stored distance (diagnostic)
 
   HostEnv(const Planes& p, uint64_t cap_) : P(p), cap(cap_), keys(cap_ + 1, S2_KEY_EMPTY), stamps(cap_ + 1, 0), recs((cap_ + 1) * 16, 0) {
     for (auto& x : st) x = 0;
@@ -149,7 +150,7 @@ struct HostEnv {
     }
     uint64_t h = tbl_home(key);
     while (true) {
-      if (keys[h] == S2_KEY_EMPTY) { keys[h] = key; *created = true; n_entries++; return (int)h; }
+      if (keys[h] == S2_KEY_EMPTY) { keys[h] = key; *created = true; changed = true; n_entries++; return (int)h; }
       if (keys[h] == key) { *created = false; return (int)h; }
       h = tbl_next(h);
     }
@@ -160,7 +161,7 @@ struct HostEnv {
   void update(int slot, int idx, int length) {
     uint32_t& d = recs[(size_t)slot * 16 + idx];
     const uint32_t v = (uint32_t)length & 0xffu;
-    if (v > d) d = v;
+    if (v > d) { d = v; changed = true; }
   }
   void link(int slot, int idx) { recs[(size_t)slot * 16 + 5] |= 1u << idx; }
   uint32_t dist_now(int slot, int idx) const { return recs[(size_t)slot * 16 + idx]; }
@@ -187,7 +188,8 @@ struct s2h_stats { uint64_t n_junctions, nb_jcheck_kmer, nb_no_juncs, nb_process
 // returns 0, or -1 when a line is too long for the thread path
 int s2h_scan(const char* text, size_t n, int fastq, int paired, int no_cleaning, int k, int j, int spacer,
              const uint8_t* bloo2, int log2_tai, int n_hash, uint8_t* short_pf, int spf_log2, int spf_nh,
-             uint8_t* long_pf, int lpf_log2, int lpf_nh, s2h_rec** recs_out, uint64_t* n_out, s2h_stats* stats) {
+             uint8_t* long_pf, int lpf_log2, int lpf_nh, s2h_rec** recs_out, uint64_t* n_out, s2h_stats* stats,
+             uint64_t* quiet_profile /* NULL, or 20 counters: records per 5 % of the stream that changed visible state */) {
   HostBits bloom{bloo2, (1ull << log2_tai) - 1, n_hash};
   Planes P;
   build_planes(text, n, fastq, k, j, bloom, P);
@@ -209,7 +211,9 @@ int s2h_scan(const char* text, size_t n, int fastq, int paired, int no_cleaning,
     s2_lookup_line(e, L, ls, n_pos > 0 ? n_pos : 0);
     e.rec = (uint32_t)r; e.part = 0;
     e.stamp_next = (unsigned long long)r << 20;
+    e.changed = false;
     s2_line(e, L, ls, le);
+    if (quiet_profile && e.changed) quiet_profile[r * 20 / P.seq_start.size()]++;
     if (e.want_ext && !e.ext_buf.empty()) e.ext_flush();
   }
   if (e.want_ext) lpf.process_batch(e.ext.data(), e.ext.size(), (uint32_t)P.seq_start.size(), 0);

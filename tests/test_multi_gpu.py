@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_job_on_gpus(tmp_path, world):
     import faucet_b200 as fb
     if fb.device_count() < world:

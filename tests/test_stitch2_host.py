@@ -35,7 +35,7 @@ def _run(lib, text, fastq, paired, no_cleaning, k, j, spacer, bloo2, lt, nh, spf
     p = lambda a: None if a is None else a.ctypes.data_as(u8)
     rc = lib.s2h_scan(C.c_char_p(text), C.c_size_t(len(text)), int(fastq), int(paired), int(no_cleaning), k, j, spacer,
                       p(bloo2), lt, nh, p(spf), spf_geom[0], spf_geom[1], p(lpf), lpf_geom[0], lpf_geom[1],
-                      C.byref(recs), C.byref(n), C.byref(st))
+                      C.byref(recs), C.byref(n), C.byref(st), None)
     assert rc == 0
     arr = np.zeros(n.value, REC_DTYPE)
     if n.value:
