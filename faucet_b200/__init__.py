@@ -6,8 +6,8 @@ used by tests/ and bench.py; it holds no compute and has no CPU fallback.
 """
 from ._lib import (FaucetError, JunctionRec, LoadStats, ScanStats, Session, device_count, geometry_2_hash,
                    geometry_from_reads, geometry_optimal, lib, load_two_filters, load_two_filters_mem, plan_shards, scan,
-                   scan_mem, set_batch_bytes, set_epoch_limit, set_tuning, timings, REC_DTYPE)
+                   scan_mem, scan_retained, set_batch_bytes, set_epoch_limit, set_tuning, timings, REC_DTYPE)
 
 __all__ = ["FaucetError", "JunctionRec", "LoadStats", "ScanStats", "Session", "device_count", "geometry_2_hash",
            "geometry_from_reads", "geometry_optimal", "lib", "load_two_filters", "load_two_filters_mem", "plan_shards", "scan",
-           "scan_mem", "set_batch_bytes", "set_epoch_limit", "set_tuning", "timings", "REC_DTYPE"]
+           "scan_mem", "scan_retained", "set_batch_bytes", "set_epoch_limit", "set_tuning", "timings", "REC_DTYPE"]

@@ -70,6 +70,7 @@ def _load():
                  _u8p, C.c_int, C.c_int, _recpp, _u64p, C.POINTER(ScanStats)]
     L.faucet_gpu_scan.argtypes = [C.c_char_p] + scan_tail
     L.faucet_gpu_scan_mem.argtypes = [C.c_void_p, C.c_size_t] + scan_tail
+    L.faucet_gpu_scan_retained.argtypes = scan_tail[1:]  # no text and no fastq flag: the retained planes know
     L.faucet_gpu_free.argtypes = [C.c_void_p]
     L.faucet_gpu_set_batch_bytes.argtypes = [C.c_size_t]
     L.faucet_gpu_set_epoch_limit.argtypes = [C.c_uint64]
@@ -221,6 +222,16 @@ def scan_mem(text, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2
     _check(lib.faucet_gpu_scan_mem(addr, n, int(fastq), int(paired_ends), int(no_cleaning), k, j, max_spacer_dist,
                                    _ptr(bloo2), log2_tai, n_hash, _ptr(spf), spf_geom[0], spf_geom[1], _ptr(lpf),
                                    lpf_geom[0], lpf_geom[1], C.byref(recs), C.byref(cnt), C.byref(st)))
+    return _take_recs(recs, cnt), st.as_dict()
+
+
+def scan_retained(paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, log2_tai, n_hash, spf=None, spf_geom=(0, 0),
+                  lpf=None, lpf_geom=(0, 0)):
+    """pass 2 over the planes the last load_two_filters[_mem] left in HBM (set_tuning("retain_planes", 1) before it)"""
+    recs, cnt, st = C.POINTER(JunctionRec)(), C.c_uint64(), ScanStats()
+    _check(lib.faucet_gpu_scan_retained(int(paired_ends), int(no_cleaning), k, j, max_spacer_dist, _ptr(bloo2), log2_tai,
+                                        n_hash, _ptr(spf), spf_geom[0], spf_geom[1], _ptr(lpf), lpf_geom[0], lpf_geom[1],
+                                        C.byref(recs), C.byref(cnt), C.byref(st)))
     return _take_recs(recs, cnt), st.as_dict()
 
 

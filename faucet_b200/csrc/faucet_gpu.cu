@@ -35,6 +35,8 @@ struct Global {
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
   int stitch_impl = 1;    // 1: one warp per record (stitch.cuh, the faster one as measured); 2: one thread walks a record (stitch2.cuh)
   size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
+  bool retain_planes = false;         // pass 1 keeps the parsed planes of every batch in HBM for faucet_gpu_scan_retained
+  size_t retain_budget = (size_t)64 << 30;
   unsigned long long ext_cap0 = 1ull << 24;
   size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
   faucet_timings tim{};
@@ -109,6 +111,14 @@ struct faucet_session {
   std::vector<faucet_junction_rec> recs_out;
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
+  // planes of the batches of the last pass 1 (tuning "retain_planes"): pass 2 can run without the text
+  struct Retained { size_t n; uint32_t n_recs; bool fastq; uint32_t *inval, *packed, *seq_start, *seq_end; };
+  std::vector<Retained> retained;
+  struct Arena { uint8_t* p; size_t cap, used; };  // device blocks the retained planes live in; kept across passes
+  std::vector<Arena> arena;
+  size_t retained_bytes = 0;
+  bool retained_valid = false;
+  uint64_t retained_lines = 0;
   int impl = 0;                 // stitch kernel this session's flag buffer is laid out for (g.stitch_impl at creation)
   uint32_t* d_rows = nullptr;   // stitch2: reservation rows of the records [row_base, row_end)
   size_t rows_cap = 0;
@@ -266,6 +276,10 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "stitch_impl") {
     if (value != 1 && value != 2) return fail(FAUCET_E_ARG, "stitch_impl must be 1 (warp per record) or 2 (thread per record)");
     g.stitch_impl = (int)value;
+  } else if (n == "retain_planes") {
+    g.retain_planes = value != 0;
+  } else if (n == "retain_budget") {
+    g.retain_budget = (size_t)value;
   } else if (n == "rows_max") {
     if (value < 1 || value > ((uint64_t)1 << 26)) return fail(FAUCET_E_ARG, "rows_max out of range");
     g.rows_max = (size_t)value;
@@ -331,6 +345,8 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   return 0;
 }
 
+static void retained_free(faucet_session* s);
+
 void faucet_session_destroy(faucet_session* s) {
   if (!s) return;
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -340,6 +356,7 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
+  retained_free(s);
   cudaFree(s->d_rows); cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
   cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
@@ -988,6 +1005,52 @@ int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_rec
 
 // ---- whole-pass entry points ---------------------------------------------------------------------
 
+static void retained_clear(faucet_session* s) {  // forgets the planes, keeps the device blocks for the next pass 1
+  s->retained.clear();
+  for (auto& a : s->arena) a.used = 0;
+  s->retained_bytes = 0;
+  s->retained_valid = false;
+}
+static void retained_free(faucet_session* s) {
+  retained_clear(s);
+  for (auto& a : s->arena) cudaFree(a.p);
+  s->arena.clear();
+}
+static uint32_t* retained_alloc(faucet_session* s, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  for (auto& a : s->arena)
+    if (a.cap - a.used >= bytes) { uint8_t* p = a.p + a.used; a.used += bytes; return reinterpret_cast<uint32_t*>(p); }
+  size_t have = 0;
+  for (auto& a : s->arena) have += a.cap;
+  if (have + bytes > g.retain_budget) return nullptr;
+  // a new block: at least what is asked, normally 1 GiB (cudaMalloc synchronises the device, so blocks are few and kept)
+  const size_t cap = std::max(bytes, std::min<size_t>((size_t)1 << 30, g.retain_budget - have));
+  uint8_t* p = nullptr;
+  if (cudaMalloc((void**)&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  s->arena.push_back({p, cap, bytes});
+  return reinterpret_cast<uint32_t*>(p);
+}
+
+// keeps a copy of the parsed planes of the current batch (D2D, on the session stream)
+static int retained_push(faucet_session* s) {
+  const size_t n_chunks = std::max<size_t>(1, (s->n + PARSE_CHUNK - 1) / PARSE_CHUNK);
+  const size_t words = n_chunks * (PARSE_CHUNK / 32) + 2;  // what parse_batch covers, guard words included
+  const size_t nrec = std::max<size_t>(1, s->n_recs);
+  faucet_session::Retained b{s->n, s->n_recs, s->fastq, nullptr, nullptr, nullptr, nullptr};
+  if (!(b.inval = retained_alloc(s, words * 4)) || !(b.packed = retained_alloc(s, (2 * words + 2) * 4)) ||
+      !(b.seq_start = retained_alloc(s, nrec * 4)) || !(b.seq_end = retained_alloc(s, nrec * 4))) {
+    retained_clear(s);
+    return 1;  // not an error: pass 2 will need the text again
+  }
+  cudaMemcpyAsync(b.inval, s->d_inval, words * 4, cudaMemcpyDeviceToDevice, s->stream);
+  cudaMemcpyAsync(b.packed, s->d_packed, (2 * words + 2) * 4, cudaMemcpyDeviceToDevice, s->stream);
+  cudaMemcpyAsync(b.seq_start, s->d_seq_start, nrec * 4, cudaMemcpyDeviceToDevice, s->stream);
+  cudaMemcpyAsync(b.seq_end, s->d_seq_end, nrec * 4, cudaMemcpyDeviceToDevice, s->stream);
+  s->retained.push_back(b);
+  s->retained_bytes += (3 * words + 2 + 2 * nrec) * 4;
+  return 0;
+}
+
 static int get_session(faucet_session** out, int k, int log2_tai, int n_hash, int j, int spacer) {
   faucet_session* c = g.cached;
   if (c && c->k == k && c->log2_tai == log2_tai && c->n_hash == n_hash && c->cap >= g.batch_bytes + TAIL_MAX) {
@@ -1057,9 +1120,16 @@ int faucet_gpu_load_two_filters_mem(const char* text, size_t n, int fastq, int k
   if (rc) return rc;
   if ((rc = ensure_load_buffers(s)) || (rc = faucet_session_reset_filters(s))) return rc;
   uint64_t total_lines = 0;
+  retained_clear(s);
+  bool keep = g.retain_planes;
   rc = for_each_batch(s, text, n, fastq != 0, &total_lines,
-                      [&](const uint8_t*, size_t, size_t, bool) { return faucet_session_load(s); });
-  if (rc) return rc;
+                      [&](const uint8_t*, size_t, size_t, bool) {
+                        int r = faucet_session_load(s);
+                        if (!r && keep && retained_push(s)) keep = false;
+                        return r;
+                      });
+  if (rc) { retained_clear(s); return rc; }
+  s->retained_valid = keep && g.retain_planes;
   if ((rc = faucet_session_get_bloom(s, bloo2_out, bloo1_out))) return rc;
   if (stats && (rc = faucet_session_load_stats(s, stats, total_lines))) return rc;
   drain_events(s);
@@ -1086,6 +1156,36 @@ int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, 
                         if (r) return r;
                         return faucet_session_stitch_batch(s);
                       });
+  if (rc) return rc;
+  rc = faucet_session_get_junctions(s, recs_out, n_recs_out, stats);
+  drain_events(s);
+  return rc;
+}
+
+int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int max_spacer_dist, const uint8_t* bloo2,
+                             int log2_tai, int n_hash, uint8_t* short_pf, int spf_log2_tai, int spf_n_hash,
+                             uint8_t* long_pf, int lpf_log2_tai, int lpf_n_hash, faucet_junction_rec** recs_out,
+                             uint64_t* n_recs_out, faucet_scan_stats* stats) {
+  if (j < 0 || j > MAX_J) return fail(FAUCET_E_ARG, "j must be in [0,4]");
+  faucet_session* s = g.cached;
+  if (!s || !s->retained_valid || s->k != k || s->log2_tai != log2_tai || s->n_hash != n_hash)
+    return fail(FAUCET_E_STATE, "no retained planes for this geometry: run faucet_gpu_load_two_filters_mem with the "
+                                "\"retain_planes\" tuning set (and within \"retain_budget\"), or use faucet_gpu_scan_mem");
+  s->j = j; s->max_spacer = max_spacer_dist;
+  int rc;
+  if ((rc = ensure_scan_buffers(s))) return rc;
+  if (bloo2) { if ((rc = faucet_session_set_bloom(s, bloo2))) return rc; }  // NULL: the device copy pass 1 left behind
+  if ((rc = faucet_session_stitch_begin(s, paired_ends, no_cleaning, short_pf, spf_log2_tai, spf_n_hash, long_pf,
+                                        lpf_log2_tai, lpf_n_hash)))
+    return rc;
+  uint32_t *inval = s->d_inval, *packed = s->d_packed, *ss = s->d_seq_start, *se = s->d_seq_end;
+  for (auto& b : s->retained) {  // the session's plane pointers visit the retained batches in stream order
+    s->d_inval = b.inval; s->d_packed = b.packed; s->d_seq_start = b.seq_start; s->d_seq_end = b.seq_end;
+    s->n = b.n; s->n_recs = b.n_recs; s->fastq = b.fastq; s->parsed = true;
+    if ((rc = faucet_session_scan_flags(s)) || (rc = faucet_session_stitch_batch(s))) break;
+  }
+  s->d_inval = inval; s->d_packed = packed; s->d_seq_start = ss; s->d_seq_end = se;
+  s->parsed = false;
   if (rc) return rc;
   rc = faucet_session_get_junctions(s, recs_out, n_recs_out, stats);
   drain_events(s);

@@ -685,11 +685,12 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
       bool mine;
       if (n_res <= RES_CAP) {
         bool ok = true;
-        for (int i = lane; i < n_res; i += 32)
-          if (__ldcg(a.res + S->reskey[i]) != rec) ok = false;
+        for (int i = lane; i < n_res; i += 32) {  // check and release in one trip: only the holder ever rewrites a slot
+          uint32_t* slot = a.res + S->reskey[i];
+          if (__ldcg(slot) != rec) ok = false;
+          else __stcg(slot, RES_FREE);
+        }
         mine = __all_sync(0xffffffffu, ok);
-        for (int i = lane; i < n_res; i += 32)
-          if (__ldcg(a.res + S->reskey[i]) == rec) __stcg(a.res + S->reskey[i], RES_FREE);
       } else {
         mine = line_reservations<1, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
         line_reservations<2, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);

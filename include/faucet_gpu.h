@@ -100,6 +100,17 @@ int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, 
                         uint8_t* short_pf, int spf_log2_tai, int spf_n_hash, uint8_t* long_pf,
                         int lpf_log2_tai, int lpf_n_hash, faucet_junction_rec** recs_out,
                         uint64_t* n_recs_out, faucet_scan_stats* stats);
+/* Pass 2 WITHOUT the text: after faucet_gpu_load_two_filters[_mem] ran with the "retain_planes" tuning set,
+ * the parsed planes of every batch of that stream (validity bits, 2-bit codes, record table: 3/8 byte per
+ * text byte) are still in HBM, so the scan of the SAME stream -- what src/Faucet.cpp:220,241-245 does when
+ * -read_scan_file is not given -- needs no second upload and no second parse.  bloo2 may be NULL (the device
+ * copy pass 1 left behind is used).  FAUCET_E_STATE when nothing (or too much: "retain_budget" bytes) was
+ * retained; the caller then falls back to faucet_gpu_scan[_mem]. */
+int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int max_spacer_dist,
+                             const uint8_t* bloo2, int log2_tai, int n_hash, uint8_t* short_pf,
+                             int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai,
+                             int lpf_n_hash, faucet_junction_rec** recs_out, uint64_t* n_recs_out,
+                             faucet_scan_stats* stats);
 void faucet_gpu_free(void* p);
 
 /* ---- tuning / introspection -------------------------------------------------------------- */

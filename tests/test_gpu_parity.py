@@ -287,3 +287,37 @@ def test_load_sub_batches(fb, oracle, small_fq, sub0, sub):
         fb.set_tuning("load_sub_bytes", 64 << 20)
     assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
     assert gst.kmers == ost.kmers and gst.unambiguous_reads == ost.unambiguous_reads
+
+
+def test_scan_retained_matches_scan_mem(fb, oracle, small_fq, impl):
+    """pass 2 on the planes pass 1 left in HBM (no text, no second parse) == pass 2 on the text == the oracle;
+    several batches, both pair filters"""
+    _, text = small_fq
+    k, j = 31, 1
+    lt, nh = _geom(oracle, 100000, 50000)
+    sg, lg = oracle.geometry_optimal(100000 // 20, 0.01), oracle.geometry_optimal(100000 // 10, 0.01)
+    ospf, olpf = np.zeros((1 << sg[0]) // 8, np.uint8), np.zeros((1 << lg[0]) // 8, np.uint8)
+    gspf, glpf = ospf.copy(), olpf.copy()
+    _, o2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    orecs, ost = oracle.scan(text, True, True, 0, k, j, 100, o2, lt, nh, ospf, sg, olpf, lg)
+    with pytest.raises(fb.FaucetError):  # nothing retained yet
+        fb.scan_retained(True, 0, k, j, 100, None, lt, nh)
+    try:
+        fb.set_tuning("retain_planes", 1)
+        fb.set_batch_bytes(900_000)
+        g2, _, _ = fb.load_two_filters_mem(text, True, k, lt, nh)
+        assert np.array_equal(g2, o2)
+        grecs, gst = fb.scan_retained(True, 0, k, j, 100, None, lt, nh, gspf, sg, glpf, lg)  # device copy of bloo2
+        assert gst == ost and _strip(grecs) == _strip(orecs)
+        assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
+        grecs, gst = fb.scan_retained(True, 1, k, j, 100, g2, lt, nh)  # again, bloo2 from the host this time
+        orecs1, ost1 = oracle.scan(text, True, True, 1, k, j, 100, o2, lt, nh)
+        assert gst == ost1 and _strip(grecs) == _strip(orecs1)
+        fb.set_tuning("retain_budget", 1000)  # too small: pass 1 still works, pass 2 must ask for the text
+        fb.load_two_filters_mem(text, True, k, lt, nh)
+        with pytest.raises(fb.FaucetError):
+            fb.scan_retained(True, 1, k, j, 100, None, lt, nh)
+    finally:
+        fb.set_tuning("retain_planes", 0)
+        fb.set_tuning("retain_budget", 64 << 30)
+        fb.set_batch_bytes(256 << 20)
