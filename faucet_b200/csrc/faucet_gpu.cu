@@ -66,9 +66,9 @@ struct faucet_session {
   cudaStream_t stream = nullptr;
   // batch text: two buffers so that the H2D copy of the next batch (copy stream) overlaps the kernels
   // of the current one (whole-pass entry points); the second one is allocated on first use
-  uint8_t* d_textbufs[2] = {nullptr, nullptr};
+  uint8_t* d_textbufs[3] = {nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr};
   uint8_t* d_text = nullptr;  // the current batch
   size_t n = 0;               // bytes in the current batch
   bool fastq = false, parsed = false, final_batch = true;
@@ -339,8 +339,7 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   cudaMemsetAsync(s->d_textbufs[0], '\n', s->cap + TEXT_PAD, s->stream);
   s->d_text = s->d_textbufs[0];
   cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&s->ev_copied[0], cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&s->ev_copied[1], cudaEventDisableTiming);
+  for (int i = 0; i < 3; i++) cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
   *out = s;
   return 0;
 }
@@ -352,7 +351,7 @@ void faucet_session_destroy(faucet_session* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   drain_events(s);
   if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
-  for (int i = 0; i < 2; i++) { cudaFree(s->d_textbufs[i]); if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]); }
+  for (int i = 0; i < 3; i++) { cudaFree(s->d_textbufs[i]); if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]); }
   cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
@@ -1067,45 +1066,76 @@ static int get_session(faucet_session** out, int k, int log2_tai, int n_hash, in
 }
 
 // Feeds `text` through the session in batches cut at record boundaries.  `per_batch` runs the pass on
-// the parsed batch.  The H2D copy of batch i+1 is issued on the copy stream as soon as the parse of
-// batch i has told the host where batch i ends, so it overlaps the load / scan / stitch kernels of
-// batch i (the parse needs a host sync anyway, which also guarantees the other text buffer is free).
+// the parsed batch.
+//
+// The host text is uploaded in CHUNKS that do not depend on where records end (32 MiB ramping up to the
+// batch size, three device buffers), so the copy engine runs back to back: chunk j+1 is issued before
+// batch j is even parsed.  A device batch = [pad][tail][chunk]: the chunk always lands at offset TAIL_MAX
+// of its buffer; the tail -- the incomplete last record of the previous batch, from the cut point the
+// parse reported -- is carried over device to device right in front of it; up to 15 '#' bytes in front
+// of that make the batch start 16-byte aligned.  A batch starts on a record boundary, so those bytes only
+// lengthen a header line, which nothing reads.
 template <class F>
 static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fastq, uint64_t* total_lines, F per_batch) {
-  size_t off = 0;
   *total_lines = 0;
-  const size_t room = s->cap - TAIL_MAX;
-  int buf = 0;
-  // batches ramp up from 32 MiB so that the first, un-overlapped H2D copy is short
-  size_t ramp = std::min(room, (size_t)32 << 20);
-  size_t len = std::min(ramp, n);
-  int rc = stage_text(s, buf, text, len, cudaMemcpyHostToDevice, s->copy_stream);
-  if (rc) return rc;
-  CU(cudaEventRecord(s->ev_copied[buf], s->copy_stream));
-  while (true) {
-    const bool final_batch = off + len == n;
-    CU(cudaStreamWaitEvent(s->stream, s->ev_copied[buf], 0));
-    select_text(s, buf, len);
+  const size_t room = s->cap - TAIL_MAX - 64;
+  std::vector<std::pair<size_t, size_t>> chunks;  // (offset, length) in the host text
+  {
+    size_t ramp = std::min(room, (size_t)32 << 20), off = 0;
+    do {
+      const size_t len = std::min(ramp, n - off);
+      chunks.push_back({off, len});
+      off += len;
+      ramp = std::min(room, ramp * 2);
+    } while (off < n);
+  }
+  int rc;
+  size_t issued = 0;
+  auto issue = [&]() -> int {
+    const int b = (int)(issued % 3);
+    if (!s->d_textbufs[b]) {
+      int r = dmalloc(&s->d_textbufs[b], s->cap + TEXT_PAD);
+      if (r) return r;
+    }
+    uint8_t* dst = s->d_textbufs[b] + TAIL_MAX;
+    if (chunks[issued].second) CU(cudaMemcpyAsync(dst, text + chunks[issued].first, chunks[issued].second, cudaMemcpyHostToDevice, s->copy_stream));
+    // bytes past the end must not look like bases of a previous, longer batch
+    CU(cudaMemsetAsync(dst + chunks[issued].second, '\n', TEXT_PAD, s->copy_stream));
+    CU(cudaEventRecord(s->ev_copied[b], s->copy_stream));
+    issued++;
+    return 0;
+  };
+  if ((rc = issue())) return rc;
+  const uint8_t* tail_src = nullptr;  // device address of the previous batch's unconsumed tail
+  size_t tail_len = 0;
+  for (size_t j = 0; j < chunks.size(); j++) {
+    // buffer (j+1) % 3 last held batch j-2, whose kernels completed before the parse of batch j-1 returned
+    if (issued == j + 1 && issued < chunks.size() && (rc = issue())) return rc;
+    const int b = (int)(j % 3);
+    const bool final_batch = j + 1 == chunks.size();
+    CU(cudaStreamWaitEvent(s->stream, s->ev_copied[b], 0));
+    uint8_t* chunk0 = s->d_textbufs[b] + TAIL_MAX;
+    uint8_t* start = chunk0 - tail_len;
+    const size_t pad = (size_t)(reinterpret_cast<uintptr_t>(start) & 15);
+    if (tail_len) CU(cudaMemcpyAsync(start, tail_src, tail_len, cudaMemcpyDeviceToDevice, s->stream));
+    if (pad) CU(cudaMemsetAsync(start - pad, '#', pad, s->stream));
+    s->d_text = start - pad;
+    s->n = pad + tail_len + chunks[j].second;
+    s->parsed = false;
     if ((rc = parse_batch(s, fastq, final_batch))) return rc;
-    size_t consumed = len;
+    size_t consumed = s->n;
     if (!final_batch) {
       if (s->h_pctr.cut == 0) return fail(FAUCET_E_ARG, "a single record does not fit in one batch");
       consumed = (size_t)s->h_pctr.cut;
+      if (s->n - consumed > TAIL_MAX - 64) return fail(FAUCET_E_ARG, "a single record does not fit in one batch");
       uint64_t lines = s->h_pctr.total_newlines;
       *total_lines += lines - (lines % (fastq ? 4 : 2));
-      // next batch -> the other buffer, while this one is being processed
-      ramp = std::min(room, ramp * 2);
-      const size_t noff = off + consumed, nlen = std::min(ramp, n - noff);
-      if ((rc = stage_text(s, buf ^ 1, text + noff, nlen, cudaMemcpyHostToDevice, s->copy_stream))) return rc;
-      CU(cudaEventRecord(s->ev_copied[buf ^ 1], s->copy_stream));
+      tail_src = s->d_text + consumed;
+      tail_len = s->n - consumed;
     } else {
-      *total_lines += s->h_pctr.total_newlines + ((len > 0 && text[off + len - 1] != '\n') ? 1 : 0);
+      *total_lines += s->h_pctr.total_newlines + ((n > 0 && text[n - 1] != '\n') ? 1 : 0);
     }
-    if ((rc = per_batch((const uint8_t*)text + off, (size_t)0, consumed, final_batch))) return rc;
-    if (final_batch) break;
-    off += consumed;
-    len = std::min(ramp, n - off);
-    buf ^= 1;
+    if ((rc = per_batch((const uint8_t*)text + chunks[j].first, (size_t)0, consumed, final_batch))) return rc;
   }
   return 0;
 }

@@ -1,0 +1,15 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_all.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu_all.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_v11.json 2> gpurun_out/bench_err.log; echo "bench rc=$?"; python - <<'PY'
+import json
+for l in open('gpurun_out/bench_r1_v11.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value']/1e9, d['ms_per_step'], d['e2e'], d['kernels_ms_per_step'])
+PY
+FAUCET_BENCH_TWO_UPLOADS=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1_v11_two.json 2>> gpurun_out/bench_err.log; python - <<'PY'
+import json
+for l in open('gpurun_out/bench_r1_v11_two.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print("two uploads:", d['e2e'])
+PY
+tail -3 gpurun_out/bench_err.log
