@@ -2,6 +2,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -119,6 +122,8 @@ struct faucet_session {
   size_t retained_bytes = 0;
   bool retained_valid = false;
   uint64_t retained_lines = 0;
+  char* h_stage[3] = {nullptr, nullptr, nullptr};  // pinned staging buffers of the file reader (whole-pass entry points)
+  size_t h_stage_cap = 0;
   int impl = 0;                 // stitch kernel this session's flag buffer is laid out for (g.stitch_impl at creation)
   uint32_t* d_rows = nullptr;   // stitch2: reservation rows of the records [row_base, row_end)
   size_t rows_cap = 0;
@@ -356,6 +361,7 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
   retained_free(s);
+  for (int i = 0; i < 3; i++) if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
   cudaFree(s->d_rows); cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
   cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
@@ -1065,7 +1071,106 @@ static int get_session(faucet_session** out, int k, int log2_tai, int n_hash, in
   return 0;
 }
 
-// Feeds `text` through the session in batches cut at record boundaries.  `per_batch` runs the pass on
+// ---- where the read text comes from: host memory, or a file streamed through pinned buffers -------
+struct TextSource {
+  size_t n = 0;               // total bytes
+  bool ends_with_newline = true;
+  virtual ~TextSource() {}
+  virtual void plan(const std::vector<std::pair<size_t, size_t>>&) {}
+  virtual bool ready(size_t) { return true; }                       // chunk j can be acquired without blocking
+  virtual const char* acquire(size_t j, size_t off, size_t len) = 0;  // host bytes of chunk j (NULL: I/O error)
+  virtual void release(size_t) {}                                    // the H2D copy of chunk j has completed
+};
+struct MemSource : TextSource {
+  const char* text;
+  MemSource(const char* t, size_t n_) : text(t) { n = n_; ends_with_newline = n_ == 0 || t[n_ - 1] == '\n'; }
+  const char* acquire(size_t, size_t off, size_t) override { return text + off; }
+};
+// A reader thread freads chunk after chunk into three pinned buffers (kept by the session), at most three
+// chunks ahead of the uploads: disk I/O, host-to-device copies and kernels overlap, host memory stays
+// O(batch) whatever the size of the file (BASELINE configs[4]: ~200 GB of reads).
+struct FileSource : TextSource {
+  faucet_session* s;
+  FILE* f = nullptr;
+  std::vector<std::pair<size_t, size_t>> chunks;
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t n_ready = 0, n_freed = 0;
+  bool stop = false, io_error = false, alloc_error = false;
+  FileSource(faucet_session* s_, const char* path) : s(s_) {
+    f = fopen(path, "rb");
+    // the reference opens the ifstream unchecked and simply sees zero reads (utils/Bloom.cpp:268-269)
+    if (!f) return;
+    if (fseeko(f, 0, SEEK_END) == 0) {
+      const off_t sz = ftello(f);
+      if (sz > 0) {
+        n = (size_t)sz;
+        char last = '\n';
+        if (fseeko(f, sz - 1, SEEK_SET) == 0 && fread(&last, 1, 1, f) == 1) ends_with_newline = last == '\n';
+      }
+    }
+    fseeko(f, 0, SEEK_SET);
+  }
+  ~FileSource() override {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+    if (f) fclose(f);
+  }
+  void plan(const std::vector<std::pair<size_t, size_t>>& c) override {
+    chunks = c;
+    size_t need = 1;
+    for (auto& x : chunks) need = std::max(need, x.second);
+    if (need > s->h_stage_cap) {
+      for (int i = 0; i < 3; i++) { if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]); s->h_stage[i] = nullptr; }
+      s->h_stage_cap = 0;
+      for (int i = 0; i < 3; i++)
+        if (cudaHostAlloc((void**)&s->h_stage[i], need, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); alloc_error = true; return; }
+      s->h_stage_cap = need;
+    }
+    th = std::thread([this] {
+      for (size_t j = 0; j < chunks.size(); j++) {
+        {
+          std::unique_lock<std::mutex> l(mu);
+          cv.wait(l, [&] { return stop || j < n_freed + 3; });
+          if (stop) return;
+        }
+        const size_t len = chunks[j].second;
+        const bool ok = len == 0 || (f && fread(s->h_stage[j % 3], 1, len, f) == len);
+        {
+          std::lock_guard<std::mutex> l(mu);
+          if (!ok) io_error = true;
+          n_ready = j + 1;
+        }
+        cv.notify_all();
+        if (!ok) return;
+      }
+    });
+  }
+  bool ready(size_t j) override {
+    std::lock_guard<std::mutex> l(mu);
+    return n_ready > j || io_error || alloc_error;
+  }
+  const char* acquire(size_t j, size_t, size_t) override {
+    if (alloc_error) return nullptr;
+    std::unique_lock<std::mutex> l(mu);
+    cv.wait(l, [&] { return n_ready > j || io_error; });
+    return io_error ? nullptr : s->h_stage[j % 3];
+  }
+  void release(size_t j) override {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      n_freed = std::max(n_freed, j + 1);
+    }
+    cv.notify_all();
+  }
+};
+
+// Feeds the text through the session in batches cut at record boundaries.  `per_batch` runs the pass on
 // the parsed batch.
 //
 // The host text is uploaded in CHUNKS that do not depend on where records end (32 MiB ramping up to the
@@ -1076,10 +1181,11 @@ static int get_session(faucet_session** out, int k, int log2_tai, int n_hash, in
 // of that make the batch start 16-byte aligned.  A batch starts on a record boundary, so those bytes only
 // lengthen a header line, which nothing reads.
 template <class F>
-static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fastq, uint64_t* total_lines, F per_batch) {
+static int for_each_batch(faucet_session* s, TextSource& src, bool fastq, uint64_t* total_lines, F per_batch) {
   *total_lines = 0;
+  const size_t n = src.n;
   const size_t room = s->cap - TAIL_MAX - 64;
-  std::vector<std::pair<size_t, size_t>> chunks;  // (offset, length) in the host text
+  std::vector<std::pair<size_t, size_t>> chunks;  // (offset, length) in the text
   {
     size_t ramp = std::min(room, (size_t)32 << 20), off = 0;
     do {
@@ -1089,6 +1195,7 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
       ramp = std::min(room, ramp * 2);
     } while (off < n);
   }
+  src.plan(chunks);
   int rc;
   size_t issued = 0;
   auto issue = [&]() -> int {
@@ -1098,7 +1205,9 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
       if (r) return r;
     }
     uint8_t* dst = s->d_textbufs[b] + TAIL_MAX;
-    if (chunks[issued].second) CU(cudaMemcpyAsync(dst, text + chunks[issued].first, chunks[issued].second, cudaMemcpyHostToDevice, s->copy_stream));
+    const char* host = src.acquire(issued, chunks[issued].first, chunks[issued].second);
+    if (!host && chunks[issued].second) return fail(FAUCET_E_IO, "cannot read the reads file (or pin its staging buffers)");
+    if (chunks[issued].second) CU(cudaMemcpyAsync(dst, host, chunks[issued].second, cudaMemcpyHostToDevice, s->copy_stream));
     // bytes past the end must not look like bases of a previous, longer batch
     CU(cudaMemsetAsync(dst + chunks[issued].second, '\n', TEXT_PAD, s->copy_stream));
     CU(cudaEventRecord(s->ev_copied[b], s->copy_stream));
@@ -1109,8 +1218,9 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
   const uint8_t* tail_src = nullptr;  // device address of the previous batch's unconsumed tail
   size_t tail_len = 0;
   for (size_t j = 0; j < chunks.size(); j++) {
-    // buffer (j+1) % 3 last held batch j-2, whose kernels completed before the parse of batch j-1 returned
-    if (issued == j + 1 && issued < chunks.size() && (rc = issue())) return rc;
+    // buffer (j+1) % 3 last held batch j-2, whose kernels completed before the parse of batch j-1 returned.
+    // (a file source that has not read chunk j+1 yet is not waited for here: batch j goes first)
+    if (issued == j + 1 && issued < chunks.size() && src.ready(issued) && (rc = issue())) return rc;
     const int b = (int)(j % 3);
     const bool final_batch = j + 1 == chunks.size();
     CU(cudaStreamWaitEvent(s->stream, s->ev_copied[b], 0));
@@ -1123,6 +1233,7 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
     s->n = pad + tail_len + chunks[j].second;
     s->parsed = false;
     if ((rc = parse_batch(s, fastq, final_batch))) return rc;
+    src.release(j);  // the parse has synchronised the stream, which waited for the copy of chunk j
     size_t consumed = s->n;
     if (!final_batch) {
       if (s->h_pctr.cut == 0) return fail(FAUCET_E_ARG, "a single record does not fit in one batch");
@@ -1133,31 +1244,30 @@ static int for_each_batch(faucet_session* s, const char* text, size_t n, bool fa
       tail_src = s->d_text + consumed;
       tail_len = s->n - consumed;
     } else {
-      *total_lines += s->h_pctr.total_newlines + ((n > 0 && text[n - 1] != '\n') ? 1 : 0);
+      *total_lines += s->h_pctr.total_newlines + ((n > 0 && !src.ends_with_newline) ? 1 : 0);
     }
-    if ((rc = per_batch((const uint8_t*)text + chunks[j].first, (size_t)0, consumed, final_batch))) return rc;
+    if ((rc = per_batch(consumed, final_batch))) return rc;
+    if (issued == j + 1 && issued < chunks.size() && (rc = issue())) return rc;  // now it may block on the disk
   }
   return 0;
 }
 
-extern "C" {
-
-int faucet_gpu_load_two_filters_mem(const char* text, size_t n, int fastq, int k, int log2_tai, int n_hash,
-                                    uint8_t* bloo2_out, uint8_t* bloo1_out, faucet_load_stats* stats) {
+static int load_pass(TextSource& src, int fastq, int k, int log2_tai, int n_hash, uint8_t* bloo2_out, uint8_t* bloo1_out,
+                     faucet_load_stats* stats, faucet_session** s_out) {
   if (!bloo2_out) return fail(FAUCET_E_ARG, "bloo2_out is NULL");
   faucet_session* s;
   int rc = get_session(&s, k, log2_tai, n_hash, 0, 0);
   if (rc) return rc;
+  *s_out = s;
   if ((rc = ensure_load_buffers(s)) || (rc = faucet_session_reset_filters(s))) return rc;
   uint64_t total_lines = 0;
   retained_clear(s);
   bool keep = g.retain_planes;
-  rc = for_each_batch(s, text, n, fastq != 0, &total_lines,
-                      [&](const uint8_t*, size_t, size_t, bool) {
-                        int r = faucet_session_load(s);
-                        if (!r && keep && retained_push(s)) keep = false;
-                        return r;
-                      });
+  rc = for_each_batch(s, src, fastq != 0, &total_lines, [&](size_t, bool) {
+    int r = faucet_session_load(s);
+    if (!r && keep && retained_push(s)) keep = false;
+    return r;
+  });
   if (rc) { retained_clear(s); return rc; }
   s->retained_valid = keep && g.retain_planes;
   if ((rc = faucet_session_get_bloom(s, bloo2_out, bloo1_out))) return rc;
@@ -1166,30 +1276,49 @@ int faucet_gpu_load_two_filters_mem(const char* text, size_t n, int fastq, int k
   return 0;
 }
 
-int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, int no_cleaning, int k, int j,
-                        int max_spacer_dist, const uint8_t* bloo2, int log2_tai, int n_hash, uint8_t* short_pf,
-                        int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai, int lpf_n_hash,
-                        faucet_junction_rec** recs_out, uint64_t* n_recs_out, faucet_scan_stats* stats) {
+static int scan_pass(TextSource& src, int fastq, int paired_ends, int no_cleaning, int k, int j, int max_spacer_dist,
+                     const uint8_t* bloo2, int log2_tai, int n_hash, uint8_t* short_pf, int spf_log2_tai, int spf_n_hash,
+                     uint8_t* long_pf, int lpf_log2_tai, int lpf_n_hash, faucet_junction_rec** recs_out,
+                     uint64_t* n_recs_out, faucet_scan_stats* stats, faucet_session** s_out) {
   if (!bloo2) return fail(FAUCET_E_ARG, "bloo2 is NULL");
   if (j < 0 || j > MAX_J) return fail(FAUCET_E_ARG, "j must be in [0,4]");
   faucet_session* s;
   int rc = get_session(&s, k, log2_tai, n_hash, j, max_spacer_dist);
   if (rc) return rc;
+  *s_out = s;
   if ((rc = ensure_scan_buffers(s)) || (rc = faucet_session_set_bloom(s, bloo2))) return rc;
   if ((rc = faucet_session_stitch_begin(s, paired_ends, no_cleaning, short_pf, spf_log2_tai, spf_n_hash, long_pf,
                                         lpf_log2_tai, lpf_n_hash)))
     return rc;
   uint64_t total_lines = 0;
-  rc = for_each_batch(s, text, n, fastq != 0, &total_lines,
-                      [&](const uint8_t*, size_t, size_t, bool) {
-                        int r = faucet_session_scan_flags(s);
-                        if (r) return r;
-                        return faucet_session_stitch_batch(s);
-                      });
+  rc = for_each_batch(s, src, fastq != 0, &total_lines, [&](size_t, bool) {
+    int r = faucet_session_scan_flags(s);
+    if (r) return r;
+    return faucet_session_stitch_batch(s);
+  });
   if (rc) return rc;
   rc = faucet_session_get_junctions(s, recs_out, n_recs_out, stats);
   drain_events(s);
   return rc;
+}
+
+extern "C" {
+
+int faucet_gpu_load_two_filters_mem(const char* text, size_t n, int fastq, int k, int log2_tai, int n_hash,
+                                    uint8_t* bloo2_out, uint8_t* bloo1_out, faucet_load_stats* stats) {
+  MemSource src(text, n);
+  faucet_session* s = nullptr;
+  return load_pass(src, fastq, k, log2_tai, n_hash, bloo2_out, bloo1_out, stats, &s);
+}
+
+int faucet_gpu_scan_mem(const char* text, size_t n, int fastq, int paired_ends, int no_cleaning, int k, int j,
+                        int max_spacer_dist, const uint8_t* bloo2, int log2_tai, int n_hash, uint8_t* short_pf,
+                        int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai, int lpf_n_hash,
+                        faucet_junction_rec** recs_out, uint64_t* n_recs_out, faucet_scan_stats* stats) {
+  MemSource src(text, n);
+  faucet_session* s = nullptr;
+  return scan_pass(src, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, log2_tai, n_hash, short_pf,
+                   spf_log2_tai, spf_n_hash, long_pf, lpf_log2_tai, lpf_n_hash, recs_out, n_recs_out, stats, &s);
 }
 
 int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int max_spacer_dist, const uint8_t* bloo2,
@@ -1222,39 +1351,27 @@ int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int
   return rc;
 }
 
-static int read_whole_file(const char* path, std::vector<char>* buf) {
-  FILE* f = fopen(path, "rb");
-  // the reference opens the ifstream unchecked and simply sees zero reads (utils/Bloom.cpp:268-269)
-  if (!f) { buf->clear(); return 0; }
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  if (sz < 0) { fclose(f); return fail(FAUCET_E_IO, std::string("cannot size ") + path); }
-  buf->resize((size_t)sz);
-  size_t got = sz ? fread(buf->data(), 1, (size_t)sz, f) : 0;
-  fclose(f);
-  if (got != (size_t)sz) return fail(FAUCET_E_IO, std::string("short read on ") + path);
-  return 0;
-}
-
+// The path forms stream the file: a reader thread, pinned staging buffers, O(batch) host memory.  The session
+// must exist before the FileSource (it owns the staging buffers), hence the get_session up front.
 int faucet_gpu_load_two_filters(const char* reads_path, int fastq, int k, int log2_tai, int n_hash,
                                 uint8_t* bloo2_out, uint8_t* bloo1_out, faucet_load_stats* stats) {
-  std::vector<char> buf;
-  int rc = read_whole_file(reads_path, &buf);
+  faucet_session* s = nullptr;
+  int rc = get_session(&s, k, log2_tai, n_hash, 0, 0);
   if (rc) return rc;
-  return faucet_gpu_load_two_filters_mem(buf.data(), buf.size(), fastq, k, log2_tai, n_hash, bloo2_out, bloo1_out, stats);
+  FileSource src(s, reads_path);
+  return load_pass(src, fastq, k, log2_tai, n_hash, bloo2_out, bloo1_out, stats, &s);
 }
 
 int faucet_gpu_scan(const char* reads_path, int fastq, int paired_ends, int no_cleaning, int k, int j,
                     int max_spacer_dist, const uint8_t* bloo2, int log2_tai, int n_hash, uint8_t* short_pf,
                     int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai, int lpf_n_hash,
                     faucet_junction_rec** recs_out, uint64_t* n_recs_out, faucet_scan_stats* stats) {
-  std::vector<char> buf;
-  int rc = read_whole_file(reads_path, &buf);
+  faucet_session* s = nullptr;
+  int rc = get_session(&s, k, log2_tai, n_hash, j, max_spacer_dist);
   if (rc) return rc;
-  return faucet_gpu_scan_mem(buf.data(), buf.size(), fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2,
-                             log2_tai, n_hash, short_pf, spf_log2_tai, spf_n_hash, long_pf, lpf_log2_tai, lpf_n_hash,
-                             recs_out, n_recs_out, stats);
+  FileSource src(s, reads_path);
+  return scan_pass(src, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, log2_tai, n_hash, short_pf,
+                   spf_log2_tai, spf_n_hash, long_pf, lpf_log2_tai, lpf_n_hash, recs_out, n_recs_out, stats, &s);
 }
 
 }  // extern "C"

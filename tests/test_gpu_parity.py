@@ -321,3 +321,27 @@ def test_scan_retained_matches_scan_mem(fb, oracle, small_fq, impl):
         fb.set_tuning("retain_planes", 0)
         fb.set_tuning("retain_budget", 64 << 30)
         fb.set_batch_bytes(256 << 20)
+
+
+def test_path_entry_points_stream_the_file(fb, oracle, small_fq, tmp_path):
+    """faucet_gpu_load_two_filters / faucet_gpu_scan read the file through a reader thread and pinned staging
+    buffers, chunk by chunk: many tiny chunks, a ragged last record and a missing file (= zero reads, as the
+    reference's unchecked ifstream, utils/Bloom.cpp:268-269) all match the oracle on the same bytes"""
+    p, text = small_fq
+    ragged = str(tmp_path / "ragged.fq")
+    rtext = text[:text.rfind(b"\n@") + 1] + b"@tail\nACGTACGTACGTAGCTAGCTAGCTAGCATCGATCGATCAGCTAGC"
+    open(ragged, "wb").write(rtext)
+    k, j = 31, 1
+    lt, nh = _geom(oracle, 100000, 50000)
+    try:
+        fb.set_batch_bytes(300_000)
+        for path, t in ((p, text), (ragged, rtext), (str(tmp_path / "missing.fq"), b"")):
+            o1, o2, ost = oracle.load_two_filters(t, True, k, lt, nh)
+            g2, g1, gst = fb.load_two_filters(path, True, k, lt, nh, want_bloo1=True)
+            assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+            assert gst.kmers == ost.kmers and gst.reads_processed == ost.reads_processed
+            orecs, osst = oracle.scan(t, True, True, 1, k, j, 100, o2, lt, nh)
+            grecs, gsst = fb.scan(path, True, True, 1, k, j, 100, g2, lt, nh)
+            assert gsst == osst and _strip(grecs) == _strip(orecs)
+    finally:
+        fb.set_batch_bytes(256 << 20)
