@@ -101,6 +101,7 @@ struct faucet_session {
   uint32_t* d_recs = nullptr;   // REC_WORDS u32 per slot
   unsigned long long tbl_cap = 0;
   uint32_t* d_res = nullptr;
+  uint32_t* d_resw = nullptr;   // stitch2: writers' reservations
   uint32_t* d_deferred[2] = {nullptr, nullptr};
   uint32_t w_max = 0, deferred_cap = 0;
   uint32_t* d_spf = nullptr;    // device copy of the short pair filter
@@ -363,7 +364,7 @@ void faucet_session_destroy(faucet_session* s) {
   retained_free(s);
   for (int i = 0; i < 3; i++) if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
   cudaFree(s->d_rows); cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
-  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res);
+  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res); cudaFree(s->d_resw);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   faucet_session_close_peers(s);
   cudaFree(s->d_b1local); cudaFree(s->d_hist); cudaFree(s->d_hist_sums); cudaFree(s->d_out);
@@ -666,6 +667,10 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
   }
+  if (s->impl == 2 && !s->d_resw) {
+    if ((rc = dmalloc(&s->d_resw, (size_t)1 << g.res_log2))) return rc;
+    CU(cudaMemsetAsync(s->d_resw, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+  }
   if (s->w_max > s->deferred_cap) {
     for (int i = 0; i < 2; i++) {
       cudaFree(s->d_deferred[i]); s->d_deferred[i] = nullptr;
@@ -676,6 +681,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   CU(cudaMemsetAsync(s->d_st, 0, sizeof(StitchState), s->stream));
   unsigned int w0 = std::min(g.stitch_w0, s->w_max);
   CU(cudaMemcpyAsync(&s->d_st->W, &w0, 4, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemsetAsync(s->d_st->min_w, 0xff, sizeof(s->d_st->min_w), s->stream));
   // short pair filter: adds only (src/ReadScanner.cpp:208-225) => atomicOr on a device copy
   cudaFree(s->d_spf); s->d_spf = nullptr; s->h_spf = nullptr;
   if (short_pf && !no_cleaning) {
@@ -730,7 +736,7 @@ int faucet_session_stitch_batch(faucet_session* s) {
     a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
     a.k = s->k; a.j = s->j; a.spacer = s->max_spacer; a.no_cleaning = s->no_cleaning; a.paired = s->paired;
     a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
-    a.res = s->d_res; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
+    a.res = s->d_res; a.resw = s->d_resw; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
     a.deferred[0] = s->d_deferred[0]; a.deferred[1] = s->d_deferred[1];
     a.st = s->d_st;
     a.spf = s->d_spf; a.spf_mask = s->d_spf ? ((1ull << s->spf_log2) - 1) : 0; a.spf_nh = s->spf_nh;
@@ -759,9 +765,17 @@ int faucet_session_stitch_batch(faucet_session* s) {
     int rc = check_launch("stitch");
     if (rc) return rc;
     if (status == ST_DONE) break;
-    if (status == ST_STUCK) return fail(FAUCET_E_CUDA, "stitch: a round executed no record (internal error)");
+    if (status == ST_STUCK) {
+      StitchState st;
+      cudaMemcpy(&st, s->d_st, sizeof st, cudaMemcpyDeviceToHost);
+      char msg[256];
+      snprintf(msg, sizeof msg, "stitch: a round executed no record (internal error): window %llu, writers %llu, blocked %llu, first record %llu flags %llu, round %u, W %u, min_w %u %u",
+               st.stats[SS_T_P1C], st.stats[SS_T_P2A], st.stats[SS_T_P1B], st.max_need >> 8, st.max_need & 255, st.round, st.W, st.min_w[0], st.min_w[1]);
+      return fail(FAUCET_E_CUDA, msg);
+    }
     // an aborted round leaves its reservations behind
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+    if (s->d_resw) CU(cudaMemsetAsync(s->d_resw, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
     if (status == ST_MORE_ROWS) {  // every record of [row_base, row_end) is done: list the next ones
       row_base = row_end;
       row_end = (uint32_t)std::min<size_t>(s->n_recs, (size_t)row_base + g.rows_max);

@@ -75,6 +75,9 @@ struct StitchState {             // device-resident; survives kernel launches an
   unsigned int round;
   unsigned int status;
   unsigned int special;          // the key equal to KEY_EMPTY (k = 32, all 'G') is present
+  unsigned int nb[3];            // stitch2: readers newly blocked in fix-point iteration i mod 3
+  unsigned int min_w[2];         // stitch2: smallest writer of the round (by round parity); stale values only err low
+  unsigned long long quiet_runs; // stitch2: records executed as readers
 };
 
 struct StitchArgs {
@@ -95,6 +98,7 @@ struct StitchArgs {
   unsigned long long* stamps;
   unsigned long long cap;        // power of two, < 2^31
   uint32_t* res;                 // reservation table
+  uint32_t* resw;                // stitch2: the same slots, reserved by writers only (reader / writer scheme)
   uint32_t res_mask;
   uint32_t* deferred[2];         // w_max entries each
   StitchState* st;
@@ -685,12 +689,12 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
       bool mine;
       if (n_res <= RES_CAP) {
         bool ok = true;
-        for (int i = lane; i < n_res; i += 32) {  // check and release in one trip: only the holder ever rewrites a slot
-          uint32_t* slot = a.res + S->reskey[i];
-          if (__ldcg(slot) != rec) ok = false;
-          else __stcg(slot, RES_FREE);
-        }
+        for (int i = lane; i < n_res; i += 32)
+          if (__ldcg(a.res + S->reskey[i]) != rec) ok = false;
         mine = __all_sync(0xffffffffu, ok);
+        // (release after the whole check: two runs of a line may hash to the same slot)
+        for (int i = lane; i < n_res; i += 32)
+          if (__ldcg(a.res + S->reskey[i]) == rec) __stcg(a.res + S->reskey[i], RES_FREE);
       } else {
         mine = line_reservations<1, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
         line_reservations<2, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);

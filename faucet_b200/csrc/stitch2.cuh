@@ -61,8 +61,14 @@ struct RecSlot {
   LineStage G;
   LineState L;
 };
-constexpr int S2_RPW = 16;  // records one warp may hold per round (2 lanes each); fewer records => more lanes per record
-constexpr size_t S2_SMEM = (size_t)S2_WARPS * (sizeof(WarpScratch) + S2_RPW * sizeof(RecSlot));
+constexpr int S2_RPW = 32;  // records one warp may hold per round (one lane each); fewer records => more lanes per record
+// Shared memory of one warp: its record slots, then the tail of a WarpScratch (reskey, visited, stage, st: all the
+// direct path of stitch.cuh touches).  The WarpScratch pointer is placed so that its tail lands there; its head
+// (the parking arrays of the warp-per-record kernel) overlays the record slots and is never touched here.
+constexpr size_t S2_TAIL = sizeof(WarpScratch) - offsetof(WarpScratch, reskey);
+constexpr size_t S2_WARP_BYTES = S2_RPW * sizeof(RecSlot) + S2_TAIL;
+static_assert(S2_WARP_BYTES >= sizeof(WarpScratch) && S2_WARP_BYTES % 16 == 0 && (S2_WARP_BYTES - sizeof(WarpScratch)) % 8 == 0, "smem layout");
+constexpr size_t S2_SMEM = (size_t)S2_WARPS * S2_WARP_BYTES;
 
 struct DevEnv {
   const StitchArgs& a;
@@ -95,6 +101,7 @@ struct DevEnv {
   __device__ __forceinline__ void link(int slot, int idx) const { rec_link(a, slot, idx); }
   __device__ __forceinline__ uint32_t dist_now(int slot, int idx) const { return rec_dist_now(a, slot, idx); }
   __device__ __forceinline__ void spf_pair(uint64_t k1, uint64_t k2) const { spf_add_pair(a, k1, k2); }
+  __device__ __forceinline__ bool aborted() const { return false; }
   __device__ void ext_flush() {
     // chunk = header {record:32 | part:16 | count:16} + count real-extension k-mers (pair_filter_host.hpp)
     const unsigned long long off = atomicAdd(&a.st->ext_used, (unsigned long long)n_ext + 1);
@@ -157,8 +164,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char stitch_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratch* S = reinterpret_cast<WarpScratch*>(stitch_smem) + wib;  // direct path + per-warp counters
-  RecSlot* slots = reinterpret_cast<RecSlot*>(stitch_smem + S2_WARPS * sizeof(WarpScratch)) + wib * S2_RPW;
+  unsigned char* wblock = stitch_smem + (size_t)wib * S2_WARP_BYTES;
+  RecSlot* slots = reinterpret_cast<RecSlot*>(wblock);
+  WarpScratch* S = reinterpret_cast<WarpScratch*>(wblock + S2_WARP_BYTES - sizeof(WarpScratch));  // direct path + per-warp counters
   // consecutive window slots go to different SMs: slot i belongs to warp i mod (warps of the grid)
   const uint32_t total_warps = gridDim.x * S2_WARPS;
   const uint32_t gw = (uint32_t)wib * gridDim.x + blockIdx.x;
@@ -167,14 +175,19 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
   uint32_t next = __ldcg(&st->next), W = __ldcg(&st->W), round = __ldcg(&st->round);
   if (W > a.w_max) W = a.w_max;
   if (lane < SS_COUNT) S->st[lane] = 0;
+  if (timer) { st->nb[0] = 0; st->nb[1] = 0; st->nb[2] = 0; }  // first used after the first grid barrier
   __syncwarp();
   WarpCtx c;
   c.S = S; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0; c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0;
+  StitchArgs aw = a;  // the direct path reserves through `res`: this copy makes it reserve in the writers' table
+  aw.res = a.resw;
   DevEnv e{a, a.k, a.j, a.spacer, !a.no_cleaning && a.spf != nullptr, a.ext != nullptr};
   for (int i = 0; i < S2_COUNTERS; i++) e.st[i] = 0;
   e.n_created = 0; e.n_ext = 0; e.part = 0; e.rec = 0; e.stamp_next = 0; e.G = nullptr; e.w5 = 0; e.w4 = 0;
   uint32_t status = ST_DONE;
   unsigned long long need_seen = 0;  // the largest 2 len + 2 this thread has reported
+  unsigned fix_it = 0;               // fix-point iterations so far (all threads agree): counter nb[fix_it % 3]
+  unsigned n_quiet = 0;
 
   while (true) {
     const int cur = round & 1, nxt = cur ^ 1;
@@ -186,9 +199,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       if (a.row_end < a.n_recs) status = ST_MORE_ROWS;
       break;
     }
-    // n_entries / ext_used only move in phase 2, so this snapshot is the same in every thread
+    // n_entries / ext_used only move in the execution phase, so this snapshot is the same in every thread
     const unsigned long long entries0 = __ldcg(&st->n_entries), ext0 = __ldcg(&st->ext_used);
-    if (timer) __stcg(&st->nd[nxt], 0u);
+    if (timer) { __stcg(&st->nd[nxt], 0u); __stcg(&st->min_w[nxt], RES_FREE); }
     // records per warp this round (a power of two) and lanes per record
     int lg2 = 0;
     while (((uint64_t)total_warps << lg2) < n_win) lg2++;
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
     const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (gid * G));
     const uint32_t my = gw + total_warps * (uint32_t)gid;
     RecSlot& RS = slots[gid];
-    // ---- phase 1: reservations + lookups of the group's record
+    // ---- phase 1: reservations, lookups, dry run
     const unsigned long long t0 = gtime_ns();
     const bool have = my < n_win;
     uint32_t rec = 0, ls = 0, len = 0, n_res = 0;
@@ -228,12 +241,27 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
     }
     __syncwarp();
     if (have && simple) s2_lookup_group(a, RS, ls, n_pos, lgi, G);
+    __syncwarp();
+    // the record's first lane walks the line read-only: does it change anything a later record can see?
+    bool writer = false;
+    if (have && simple && lgi == 0) {
+      e.G = &RS.G; e.w5 = ls >> 5; e.w4 = ls >> 4;
+      writer = !s2_is_quiet(e, RS.L, ls, ls + len);
+    }
+    writer = __shfl_sync(0xffffffffu, (int)writer, gid * G) != 0;
+    if (have && simple && writer)
+      for (uint32_t i = lgi; i < n_res; i += G) atomicMin(a.resw + __ldg(row + 1 + i), rec);
     const uint32_t hard_mask = __ballot_sync(0xffffffffu, have && !simple && lgi == 0);
-    for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {  // rare: the warp reserves for these records together
+    for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {  // rare: the warp reserves for these records together, as writers
       const int src = __ffs(hm) - 1;
       const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
       int n_keep = 0;
       line_reservations<0, false>(a, a.packed, ls_, len_, r_, lane, S->reskey, &n_keep);
+      line_reservations<0, false>(aw, a.packed, ls_, len_, r_, lane, S->reskey, &n_keep);
+    }
+    {  // the smallest writer of the round: readers before it can never be blocked
+      const uint32_t wmin = __reduce_min_sync(0xffffffffu, (have && lgi == 0 && (writer || !simple)) ? rec : RES_FREE);
+      if (lane == 0 && wmin != RES_FREE) atomicMin(&st->min_w[cur], wmin);
     }
     const unsigned long long t1 = gtime_ns();
     grid.sync();
@@ -243,21 +271,53 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       if (entries0 + bound > (a.cap / 4) * 3) { status = ST_GROW_TABLE; break; }
       if (a.ext && ext0 + 2 * bound + n_win > a.ext_cap) { status = ST_DRAIN_EXT; break; }
     }
-    // ---- phase 2: execute or defer
+    // ---- fix point: a reader that shares a slot with an earlier writer is blocked, and from then on counts as
+    //      a writer for the readers after it (it will be looked at again next round, against the new state)
+    bool blocked = false;
+    for (int it = 0;; it++, fix_it++) {
+      bool hit = false;
+      if (have && simple && !writer && !blocked)
+        for (uint32_t i = lgi; i < n_res; i += G)
+          if (__ldcg(a.resw + __ldg(row + 1 + i)) < rec) hit = true;
+      const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+      if (hm & gmask) {
+        blocked = true;
+        for (uint32_t i = lgi; i < n_res; i += G) atomicMin(a.resw + __ldg(row + 1 + i), rec);
+      }
+      if (lane == 0 && hm) atomicAdd(&st->nb[fix_it % 3], 1u);
+      if (timer) __stcg(&st->nb[(fix_it + 1) % 3], 0u);
+      grid.sync();
+      const bool more = __ldcg(&st->nb[fix_it % 3]) != 0;
+      if (!more) { fix_it++; break; }
+      if (it >= 24) {  // give up: only the readers before the first writer still run this round (always a valid schedule)
+        if (have && simple && !writer && rec > __ldcg(&st->min_w[cur])) blocked = true;
+        fix_it++;
+        break;
+      }
+    }
+    const unsigned long long t2a = gtime_ns();
+    // ---- execution: writers need every slot of theirs (no earlier unexecuted record of any kind shares a key);
+    //      readers that are not blocked just run.  Everybody drops the reservations it holds.
     bool bad = false;
     if (have && simple)
-      for (uint32_t i = lgi; i < n_res; i += G) {  // check and release in one trip
-        uint32_t* slot = a.res + __ldg(row + 1 + i);
-        if (__ldcg(slot) != rec) bad = true;
-        else __stcg(slot, RES_FREE);
-      }
+      for (uint32_t i = lgi; i < n_res; i += G)
+        if (__ldcg(a.res + __ldg(row + 1 + i)) != rec) bad = true;
     const uint32_t badm = __ballot_sync(0xffffffffu, bad);
-    bool mine = have && simple && !(badm & gmask);  // meaningful in the group's first lane
+    // release AFTER the whole check: two runs of a line may hash to the same slot, and a slot released by the first
+    // one must not look foreign to the second
+    if (have && simple)
+      for (uint32_t i = lgi; i < n_res; i += G) {
+        const uint32_t sl = __ldg(row + 1 + i);
+        if (__ldcg(a.res + sl) == rec) __stcg(a.res + sl, RES_FREE);
+        if ((writer || blocked) && __ldcg(a.resw + sl) == rec) __stcg(a.resw + sl, RES_FREE);
+      }
+    bool mine = have && simple && (writer ? !(badm & gmask) : !blocked);  // meaningful in the group's first lane
     for (uint32_t hm = hard_mask; hm; hm &= hm - 1) {
       const int src = __ffs(hm) - 1;
       const uint32_t r_ = __shfl_sync(0xffffffffu, rec, src), ls_ = __shfl_sync(0xffffffffu, ls, src), len_ = __shfl_sync(0xffffffffu, len, src);
       const bool m = line_reservations<1, false>(a, a.packed, ls_, len_, r_, lane, nullptr, nullptr);
       line_reservations<2, false>(a, a.packed, ls_, len_, r_, lane, nullptr, nullptr);
+      line_reservations<2, false>(aw, a.packed, ls_, len_, r_, lane, nullptr, nullptr);
       if (lane == src) mine = m;
     }
     const unsigned long long t2b = gtime_ns();
@@ -267,6 +327,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       e.G = &RS.G; e.w5 = ls >> 5; e.w4 = ls >> 4;
       s2_line(e, RS.L, ls, ls + len);
       if (e.want_ext && e.n_ext) e.ext_flush();
+      if (!writer) n_quiet++;
     }
     for (uint32_t xm = __ballot_sync(0xffffffffu, have && !simple && mine && lgi == 0); xm; xm &= xm - 1) {
       const int src = __ffs(xm) - 1;
@@ -289,7 +350,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       e.n_created = 0;
       if (lane == 0 && nc) atomicAdd(&st->n_entries, (unsigned long long)nc);
     }
-    if (timer) { S->st[SS_T_P1A] += t2b - t2; }
+    if (timer) { S->st[SS_T_P1A] += t2a - t2; S->st[SS_T_P1B] += t2b - t2a; }
     const unsigned long long t3 = gtime_ns();
     grid.sync();
     if (timer) {
@@ -297,7 +358,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
       S->st[SS_ROUNDS]++;
     }
     const uint32_t nd_next = __ldcg(&st->nd[nxt]);
-    if (nd_next >= n_win) { status = ST_STUCK; break; }  // cannot happen: the earliest record of a window always executes
+    if (nd_next >= n_win) {  // cannot happen: the earliest record of a window always executes
+      status = ST_STUCK;
+      if (have && lgi == 0) {  // post-mortem for the error message
+        atomicAdd(&st->stats[SS_T_P1C], 1ull);
+        if (writer || !simple) atomicAdd(&st->stats[SS_T_P2A], 1ull);
+        if (blocked) atomicAdd(&st->stats[SS_T_P1B], 1ull);
+        atomicMin(&st->max_need, ((unsigned long long)rec << 8) | (writer ? 1u : 0u) | (blocked ? 2u : 0u) | (simple ? 4u : 0u) | ((badm & gmask) ? 8u : 0u));
+      }
+      break;
+    }
     if (nd_next * a.shrink_den > n_win) W = W / 2 > a.w_min ? W / 2 : a.w_min;
     else if (nd_next * a.grow_den < n_win && n_win >= W) W = W * 2 < a.w_max ? W * 2 : a.w_max;
     next += n_new;
@@ -316,6 +386,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
   }
   __syncwarp();
   if (lane < SS_COUNT && S->st[lane]) atomicAdd(&st->stats[lane], S->st[lane]);
+  {
+    const unsigned nq = __reduce_add_sync(0xffffffffu, n_quiet);
+    if (lane == 0 && nq) atomicAdd(&st->quiet_runs, (unsigned long long)nq);
+  }
   if (timer) {
     __stcg(&st->next, next); __stcg(&st->W, W); __stcg(&st->round, round); __stcg(&st->status, status);
   }

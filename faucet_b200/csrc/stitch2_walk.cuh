@@ -303,6 +303,7 @@ FHD void s2_subread(E& e, LineState& L, uint32_t ls, int n_pos, uint32_t s0, int
     }
     if (slot < 0) {
       slot = e.insert(key, &created);
+      if (e.aborted()) return;
       if (created) {
         e.stamp(slot);
         s2_publish(e, L, ls, n_pos, key);
@@ -316,6 +317,7 @@ FHD void s2_subread(E& e, LineState& L, uint32_t ls, int n_pos, uint32_t s0, int
     } else {
       e.update(slot, back_idx, tp - 2 * j);
     }
+    if (e.aborted()) return;
     int dist;
     if (created) dist = 0;  // a zeroed record; back_idx != fwd_idx, so nothing written above shows here
     else if (hop >= 0) dist = hop;
@@ -338,6 +340,7 @@ FHD void s2_subread(E& e, LineState& L, uint32_t ls, int n_pos, uint32_t s0, int
     bool created = false;
     e.st[S2_NOJUNC]++;
     const int slot = e.insert(key, &created);
+    if (e.aborted()) return;
     if (created) {
       e.stamp(slot);
       s2_publish(e, L, ls, n_pos, key);
@@ -382,11 +385,57 @@ FHD void s2_line(E& e, LineState& L, uint32_t ls, uint32_t le) {
       const uint32_t b = s2_next_bit<false>(FpView<E, FP_V>{e}, a, qe);
       if ((int)(b - a) >= k) {
         s2_subread(e, L, ls, n_pos, a, (int)(b - a) + k - 1);
+        if (e.aborted()) return;
         e.st[S2_NOERR]++;
       }
       q = b;
     }
   }
+}
+
+// ---- "would this record change anything a later record can see?" --------------------------------
+// A record is QUIET against the current table if its walk creates no junction and raises no stored
+// distance: all it does is count coverage and set link flags, which no walk ever reads and which
+// commute.  Quiet records therefore commute with each other; only the others ("writers") need the
+// exclusive reservations of the schedule.  DryEnv runs the same walk read-only and stops at the first
+// visible change.
+template <class E>
+struct DryEnv {
+  const E& e;
+  int k, j, spacer;
+  bool pairs, want_ext;
+  unsigned st[S2_COUNTERS];  // discarded
+  bool quiet;
+  FHD explicit DryEnv(const E& env) : e(env), k(env.k), j(env.j), spacer(env.spacer), pairs(false), want_ext(false), quiet(true) {
+    for (int i = 0; i < S2_COUNTERS; i++) st[i] = 0;
+  }
+  FHD uint32_t inval_word(uint32_t w) const { return e.inval_word(w); }
+  FHD uint32_t fp_word(int p, uint32_t w) const { return e.fp_word(p, w); }
+  FHD uint32_t packed_word(uint32_t w) const { return e.packed_word(w); }
+  FHD int find(uint64_t key) const { return e.find(key); }
+  FHD int insert(uint64_t key, bool* created) {  // a key that is not there yet would be created: a visible change
+    *created = false;
+    const int s = e.find(key);
+    if (s < 0) { quiet = false; return 0; }
+    return s;
+  }
+  FHD void stamp(int) {}
+  FHD void add_cov(int, int) {}
+  FHD void link(int, int) {}
+  FHD void update(int slot, int idx, int length) {
+    if (((uint32_t)length & 0xffu) > e.dist_peek(slot, idx)) quiet = false;
+  }
+  FHD uint32_t dist_now(int slot, int idx) const { return e.dist_peek(slot, idx); }  // nothing of ours to be ordered after
+  FHD void spf_pair(uint64_t, uint64_t) {}
+  FHD void ext_push(uint64_t) {}
+  FHD bool aborted() const { return !quiet; }
+};
+template <class E>
+FHD bool s2_is_quiet(const E& e, LineState& L, uint32_t ls, uint32_t le) {
+  DryEnv<E> d(e);
+  s2_line(d, L, ls, le);
+  L.pstale = 0;  // the dry walk marked what it touched; the real one starts over
+  return d.quiet;
 }
 
 }  // namespace faucet

@@ -189,6 +189,7 @@ int main(int argc, char* argv[]) {
 
   // ---- Bloom filter: from reads (pass 1) or from a file ------------------------------------------
   int log2_tai = 0, n_hash = 0;
+  bool same_file = false;
   std::vector<uint8_t> bloom;
   if (o.from_bloom) {  // getBloomFilterFromFile (src/Faucet.cpp:185-195): geometry from -fp, --two_hash honoured HERE only
     if (o.two_hash ? faucet_geometry_2_hash(o.estimated_kmers, o.fpRate, &log2_tai, &n_hash)
@@ -204,6 +205,9 @@ int main(int argc, char* argv[]) {
     bloom.assign(((size_t)1 << log2_tai) / 8, 0);
     faucet_load_stats st;
     printf("Weights before load: %f, %f \n", 0.0, 0.0);
+    // one reads file for both passes (the default): pass 1 leaves the parsed planes in HBM and pass 2 runs on them
+    same_file = !o.just_load && o.read_load_file == o.read_scan_file;
+    if (same_file && faucet_gpu_set_tuning("retain_planes", 1)) die("tuning");
     if (faucet_gpu_load_two_filters(o.read_load_file.c_str(), o.fastq, o.size_kmer, log2_tai, n_hash, bloom.data(), nullptr, &st))
       die("load_two_filters");
     printf("Weights after load: %f, %f \n", st.weight1, st.weight2);
@@ -229,10 +233,15 @@ int main(int argc, char* argv[]) {
   uint64_t n = 0;
   faucet_scan_stats st;
   printf("Weight before read scan: %f \n", weight(bloom));
-  if (faucet_gpu_scan(o.read_scan_file.c_str(), o.fastq, o.paired_ends, o.no_cleaning, o.size_kmer, o.j, o.maxSpacerDist,
-                      bloom.data(), log2_tai, n_hash, spf.data(), s_log2, s_nh, o.paired_ends ? lpf.data() : nullptr, l_log2, l_nh,
-                      &recs, &n, &st))
-    die("scan");
+  int rc = FAUCET_E_STATE;
+  if (same_file)
+    rc = faucet_gpu_scan_retained(o.paired_ends, o.no_cleaning, o.size_kmer, o.j, o.maxSpacerDist, nullptr, log2_tai, n_hash,
+                                  spf.data(), s_log2, s_nh, o.paired_ends ? lpf.data() : nullptr, l_log2, l_nh, &recs, &n, &st);
+  if (rc == FAUCET_E_STATE)  // other file, or more planes than the retention budget: read the scan file
+    rc = faucet_gpu_scan(o.read_scan_file.c_str(), o.fastq, o.paired_ends, o.no_cleaning, o.size_kmer, o.j, o.maxSpacerDist,
+                         bloom.data(), log2_tai, n_hash, spf.data(), s_log2, s_nh, o.paired_ends ? lpf.data() : nullptr, l_log2, l_nh,
+                         &recs, &n, &st);
+  if (rc) die("scan");
   printf("Reads processed: %lli\n", (long long)st.reads_processed);
   printf("Unambiguous reads: %lli\n", (long long)st.unambiguous_reads);
   // ReadScanner::printScanSummary (src/ReadScanner.cpp:19-27)

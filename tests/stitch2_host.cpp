@@ -166,6 +166,7 @@ struct HostEnv {
   void link(int slot, int idx) { recs[(size_t)slot * 16 + 5] |= 1u << idx; }
   uint32_t dist_now(int slot, int idx) const { return recs[(size_t)slot * 16 + idx]; }
   void spf_pair(uint64_t k1, uint64_t k2) { spf->add_pair(k1, k2, k); }
+  bool aborted() const { return false; }
   void ext_flush() {
     ext.push_back(((uint64_t)rec << 32) | ((uint64_t)(part & 0xffffu) << 16) | ext_buf.size());
     ext.insert(ext.end(), ext_buf.begin(), ext_buf.end());
@@ -212,7 +213,9 @@ int s2h_scan(const char* text, size_t n, int fastq, int paired, int no_cleaning,
     e.rec = (uint32_t)r; e.part = 0;
     e.stamp_next = (unsigned long long)r << 20;
     e.changed = false;
+    const bool quiet = s2_is_quiet(e, L, ls, le);  // read-only dry run first: it must predict the real walk
     s2_line(e, L, ls, le);
+    if (quiet == e.changed) return -2;
     if (quiet_profile && e.changed) quiet_profile[r * 20 / P.seq_start.size()]++;
     if (e.want_ext && !e.ext_buf.empty()) e.ext_flush();
   }
