@@ -31,18 +31,29 @@ struct ParseCounters {
   unsigned int complex_overflow;
 };
 
+// bit i of the result <=> byte i of the 32-byte span satisfies the test.  A byte-wise compare leaves 0xff per
+// matching byte; (x & 0x01010101) * 0x01020408 gathers the four flags of a word into its top nibble.
+__device__ __forceinline__ uint32_t gather4(uint32_t eq) { return ((eq & 0x01010101u) * 0x01020408u) >> 24; }
 __device__ __forceinline__ uint32_t newline_mask32(const uint4 a, const uint4 b) {
-  // bit i set <=> byte i of the 32-byte span is '\n'
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) m |= gather4(__vcmpeq4(w[i], 0x0a0a0a0au)) << (4 * i);
+  return m;
+}
+// upper-case A / C / G / T (isValidNuc, utils/Kmer.cpp:50-60)
+__device__ __forceinline__ uint32_t base_mask32(const uint4 a, const uint4 b) {
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   uint32_t m = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    uint32_t eq = __vcmpeq4(w[i], 0x0a0a0a0au);  // 0xff per equal byte
-    uint32_t bits = ((eq & 0x00000001u)) | ((eq & 0x00000100u) >> 7) | ((eq & 0x00010000u) >> 14) | ((eq & 0x01000000u) >> 21);
-    m |= bits << (4 * i);
+    const uint32_t eq = __vcmpeq4(w[i], 0x41414141u) | __vcmpeq4(w[i], 0x43434343u) | __vcmpeq4(w[i], 0x47474747u) | __vcmpeq4(w[i], 0x54545454u);
+    m |= gather4(eq) << (4 * i);
   }
   return m;
 }
+// NT2int codes ((c >> 1) & 3) of four bytes, first byte in the top two bits of the returned byte
+__device__ __forceinline__ uint32_t codes4(uint32_t w) { return (((w >> 1) & 0x03030303u) * 0x40100401u) >> 24; }
 
 // text must be readable (padded) up to a multiple of PARSE_CHUNK; bytes >= n are ignored.
 __global__ void __launch_bounds__(PARSE_THREADS)
@@ -192,28 +203,37 @@ parse_planes_kernel(ParseArgs a) {
   unsigned long long quirk = ~0ull;
   if (a.final_batch && a.n > 0 && a.text[a.n - 1] != '\n' && (total_nl & pm) == 0) quirk = total_nl;
 
-  const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-  uint32_t inval = 0, pk0 = 0, pk1 = 0;
   // bytes at or past n (the CTA grid covers n rounded up to PARSE_CHUNK) come out as invalid
-  size_t lim = off >= a.n ? 0 : (a.n - off < 32 ? a.n - off : 32);
-#pragma unroll
-  for (int i = 0; i < 32; i++) {
-    uint8_t c = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-    bool seq_line = (((line & pm) == 1u) && (unsigned long long)line < complete) || (unsigned long long)line == quirk;
-    bool ok = seq_line && nt_valid(c) && (size_t)i < lim;
-    if (!ok) inval |= 1u << i;
-    uint32_t code = nt_code(c);
-    if (i < 16) pk0 |= code << (30 - 2 * i); else pk1 |= code << (30 - 2 * (i - 16));
-    if (seq_line && !ok && c != '\n' && (size_t)i < lim) parse_check_complex(a, off + i);
-    if (c == '\n' && (size_t)i < lim) {
-      if (seq_line && (line >> a.rec_shift) < a.rec_cap) a.seq_end[line >> a.rec_shift] = (uint32_t)(off + i);
+  const size_t lim = off >= a.n ? 0 : (a.n - off < 32 ? a.n - off : 32);
+  const uint32_t limmask = lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
+  auto is_seq = [&](uint32_t ln) {
+    return (((ln & pm) == 1u) && (unsigned long long)ln < complete) || (unsigned long long)ln == quirk;
+  };
+  // which bytes of the span lie on a sequence line: walk the (usually 0 or 1) newlines of the span
+  uint32_t seqm = 0;
+  {
+    uint32_t m = nlm, pos = 0;
+    while (true) {
+      const uint32_t nxt = m ? (uint32_t)(__ffs(m) - 1) : 32u;
+      const bool sq = is_seq(line);
+      if (sq && nxt > pos) seqm |= (nxt >= 32 ? 0xffffffffu : ((1u << nxt) - 1u)) & ~((1u << pos) - 1u);
+      if (nxt >= 32) break;
+      // the newline at nxt ends `line` (nlm only holds bytes below lim)
+      if (sq && (line >> a.rec_shift) < a.rec_cap) a.seq_end[line >> a.rec_shift] = (uint32_t)(off + nxt);
       line++;
-      if (!a.final_batch && (unsigned long long)line == complete && complete > 0) a.ctr->cut = off + i + 1;
-      if (((((line & pm) == 1u) && (unsigned long long)line < complete) || (unsigned long long)line == quirk) &&
-          (line >> a.rec_shift) < a.rec_cap)
-        a.seq_start[line >> a.rec_shift] = (uint32_t)(off + i + 1);
+      if (!a.final_batch && (unsigned long long)line == complete && complete > 0) a.ctr->cut = off + nxt + 1;
+      if (is_seq(line) && (line >> a.rec_shift) < a.rec_cap) a.seq_start[line >> a.rec_shift] = (uint32_t)(off + nxt + 1);
+      pos = nxt + 1;
+      m &= m - 1;
+      if (pos >= 32) break;
     }
   }
+  const uint32_t vm = base_mask32(v0, v1);
+  const uint32_t inval = ~(seqm & vm & limmask);
+  // a non-base on a sequence line (N, lower case, '\r'): the thread that owns it checks the line for several segments
+  for (uint32_t cm = seqm & ~vm & ~nlm & limmask; cm; cm &= cm - 1) parse_check_complex(a, off + (__ffs(cm) - 1));
+  const uint32_t pk0 = (codes4(v0.x) << 24) | (codes4(v0.y) << 16) | (codes4(v0.z) << 8) | codes4(v0.w);
+  const uint32_t pk1 = (codes4(v1.x) << 24) | (codes4(v1.y) << 16) | (codes4(v1.z) << 8) | codes4(v1.w);
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.final_batch && a.n > 0 && a.text[a.n - 1] != '\n') {
     // unterminated last line: it is either a sequence line or the re-used header (quirk); a quirk line
     // that is the only line of the batch starts at offset 0, which the zero-fill already says
