@@ -514,7 +514,8 @@ int faucet_session_load(faucet_session* s) {
     const int grid = (int)std::min<uint32_t>(g.sm_count * 8, (a.w_end - a.w_begin + 7) / 8);
     {
       KTimer kt(s, KT_LOAD_A);
-      DISPATCH_NH(load_A_kernel, s->n_hash, grid, LOAD_THREADS, s->stream, a);
+      const int grid_a = (int)std::min<uint32_t>(g.sm_count * LOAD_CTAS_PER_SM, (a.w_end - a.w_begin + 7) / 8);  // one full wave
+      DISPATCH_NH(load_A_kernel, s->n_hash, grid_a, LOAD_THREADS, s->stream, a);
       s->launches++;
     }
     if (a.n_complex) {

@@ -24,6 +24,7 @@ namespace faucet {
 
 constexpr uint32_t STAMP_INF = 0xffffffffu;
 constexpr int LOAD_THREADS = 256;
+constexpr int LOAD_CTAS_PER_SM = 6;  // load_A is compiled for 6 resident CTAs per SM; its grid is exactly one wave
 constexpr int MAX_NHASH = 10;  // NSEEDSBLOOM, utils/Bloom.h:40
 
 struct LoadCounters {
@@ -129,7 +130,7 @@ __device__ __forceinline__ bool load_body_B(const LoadArgs& a, uint64_t fwd, uin
 }
 
 template <int NH>
-__global__ void __launch_bounds__(LOAD_THREADS) load_A_kernel(LoadArgs a) {
+__global__ void __launch_bounds__(LOAD_THREADS, 6) load_A_kernel(LoadArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * LOAD_THREADS + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * LOAD_THREADS) >> 5;
