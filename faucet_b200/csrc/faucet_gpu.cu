@@ -591,7 +591,7 @@ int faucet_session_scan_flags(faucet_session* s) {
   a.inval = s->d_inval; a.packed = s->d_packed; a.n_words = (uint32_t)((s->n + 31) / 32);
   a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
   a.fplanes = s->impl == 2 ? reinterpret_cast<uint32_t*>(s->d_flags) : nullptr;
-  const int grid = g.sm_count * 8;
+  const int grid = g.sm_count * SCAN_CTAS_PER_SM * 2;  // two full waves of resident CTAs
   {
     KTimer kt(s, KT_SCAN);
     DISPATCH_NH(scan_flags_kernel, s->n_hash, grid, SCAN_THREADS, s->stream, a);

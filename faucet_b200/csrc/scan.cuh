@@ -30,6 +30,10 @@
 namespace faucet {
 
 constexpr int SCAN_THREADS = 256;
+#ifndef FAUCET_SCAN_CTAS
+#define FAUCET_SCAN_CTAS 4
+#endif
+constexpr int SCAN_CTAS_PER_SM = FAUCET_SCAN_CTAS;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_Q = 192;  // 32 positions x 6 alternates
 constexpr int MAX_J = 4;     // JChecker scratch arrays hold 1000 k-mers => j <= 4 (utils/JChecker.cpp:93-94)
@@ -119,7 +123,7 @@ struct ScanQueue {  // per warp
 };
 
 template <int NH>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_flags_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_kernel(ScanArgs a) {
   __shared__ ScanQueue queues[SCAN_WARPS];
   ScanQueue& q = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
