@@ -188,6 +188,9 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    for kv in filter(None, os.environ.get("FAUCET_TUNING", "").split(",")):  # experiments: name=value[,name=value]
+        name, val = kv.split("=")
+        fb.set_tuning(name, int(val))
     k = w["k"]
     _, lt, nh = fb.geometry_from_reads(w["est"], w["sing"], FP)
     # weak scaling: rank g holds shard g of ONE job = N read samples (100x each) of the same genome,
@@ -205,14 +208,39 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)
 
-    sess = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=int(cap.item()) + 4096)
+    # a device batch holds < 3 GiB of text (32-bit offsets): a bigger single-GPU workload (configs[2] at N = 1) is fed
+    # to the stage API in record-aligned parts, all of them resident in HBM
+    PART_MAX = 2 << 30
+    parts = [(0, n_text)]
+    if world == 1 and n_text > PART_MAX:
+        parts = fb.plan_shards((host.data_ptr(), n_text), True, (n_text + PART_MAX - 1) // PART_MAX)
+    part_cap = max(b - a for a, b in parts)
+    sess = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER,
+                      max_text_bytes=(int(cap.item()) if len(parts) == 1 else part_cap) + 4096)
     job = None
     if world > 1:
         from faucet_b200.multi import ShardedJob, TorchComm
         job = ShardedJob(sess, TorchComm(torch.device("cuda", local)))
         job.setup()
 
+    def step_parts(base):  # several batches through the stage API (load accumulates; one junction map)
+        sess.reset_filters()
+        for a, b in parts:
+            sess.set_text((base + a, b - a), device=True)
+            sess.parse(True)
+            sess.load()
+        sess.get_bloom(to_host=False)
+        sess.stitch_begin(True, True)
+        for a, b in parts:
+            sess.set_text((base + a, b - a), device=True)
+            sess.parse(True)
+            sess.scan_flags()
+            sess.stitch_batch()
+        return 0
+
     def step_from(src, device):
+        if len(parts) > 1:
+            return step_parts(src[0])
         sess.set_text(src, device=device)
         if job is None:
             sess.reset_filters()
@@ -330,7 +358,7 @@ def run_ours(args, w):
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["desc"], "k": k, "log2_tai": lt, "n_hash": nh, "j": J,
                        "max_spacer_dist": MAX_SPACER, "reads_per_gpu": reads, "kmers_per_pass_per_gpu": kmers_per_pass,
-                       "text_bytes_per_gpu": n_text, "junctions": int(n_junc),
+                       "text_bytes_per_gpu": n_text, "junctions": int(n_junc), "resident_batches": len(parts),
                        "l2": "inputs (%.0f MB text + planes) exceed the 126 MB L2" % (n_text / 1e6),
                        "parallelism": ("%d contiguous shards of one read stream (one per GPU): exact P2P prefix-OR / OR all-reduce "
                                        "of the Bloom filters over NVLink, junction stitch on GPU 0" % world) if world > 1 else "single GPU"},

@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
     const unsigned long long t2 = gtime_ns();
     {
       const unsigned long long bound = __ldcg(&st->max_need) * n_win;
-      if (entries0 + bound > (a.cap / 4) * 3) { status = ST_GROW_TABLE; break; }
+      if (entries0 + bound > a.cap / 2) { status = ST_GROW_TABLE; break; }
       if (a.ext && ext0 + 2 * bound + n_win > a.ext_cap) { status = ST_DRAIN_EXT; break; }
     }
     // ---- phase 2: execute or defer

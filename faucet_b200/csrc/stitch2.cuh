@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stitch2_kernel(StitchArgs a) {
     const unsigned long long t2 = gtime_ns();
     {
       const unsigned long long bound = __ldcg(&st->max_need) * n_win;
-      if (entries0 + bound > (a.cap / 4) * 3) { status = ST_GROW_TABLE; break; }
+      if (entries0 + bound > a.cap / 2) { status = ST_GROW_TABLE; break; }
       if (a.ext && ext0 + 2 * bound + n_win > a.ext_cap) { status = ST_DRAIN_EXT; break; }
     }
     // ---- fix point: a reader that shares a slot with an earlier writer is blocked, and from then on counts as
