@@ -112,7 +112,8 @@ struct faucet_session {
   std::vector<uint64_t> h_ext;
   LongPairFilter lpf;
   uint64_t rec_base = 0;        // global index of the first record of the current batch
-  std::vector<faucet_junction_rec> recs_out;
+  faucet_junction_rec* h_recs = nullptr;  // pinned staging of the collected junction map (grow-only)
+  size_t h_recs_cap = 0, n_recs_out = 0;
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
   // planes of the batches of the last pass 1 (tuning "retain_planes"): pass 2 can run without the text
@@ -363,6 +364,7 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
   retained_free(s);
   for (int i = 0; i < 3; i++) if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
+  if (s->h_recs) cudaFreeHost(s->h_recs);
   cudaFree(s->d_rows); cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
   cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res); cudaFree(s->d_resw);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
@@ -703,7 +705,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   }
   s->h_ext.clear();
   s->rec_base = 0;
-  s->recs_out.clear();
+  s->n_recs_out = 0;
   std::memset(&s->sstats, 0, sizeof s->sstats);
   s->stitching = true;
   return 0;
@@ -845,8 +847,15 @@ static int stitch_finish(faucet_session* s) {
                                                             s->d_hist, (JunctionOut*)s->d_out);
     s->launches += 5;
   }
-  s->recs_out.resize(n);
-  if (n) CU(cudaMemcpyAsync(s->recs_out.data(), s->d_out, n * sizeof(JunctionOut), cudaMemcpyDeviceToHost, s->stream));
+  if (n > s->h_recs_cap) {
+    if (s->h_recs) cudaFreeHost(s->h_recs);
+    s->h_recs = nullptr; s->h_recs_cap = 0;
+    const size_t want = n + n / 4 + 1024;
+    CU(cudaHostAlloc((void**)&s->h_recs, want * sizeof(faucet_junction_rec), cudaHostAllocDefault));
+    s->h_recs_cap = want;
+  }
+  s->n_recs_out = n;
+  if (n) CU(cudaMemcpyAsync(s->h_recs, s->d_out, n * sizeof(JunctionOut), cudaMemcpyDeviceToHost, s->stream));
   if (s->h_spf) CU(cudaMemcpyAsync(s->h_spf, s->d_spf, ((size_t)1 << s->spf_log2) / 8, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   if ((rc = check_launch("stitch_collect"))) return rc;
@@ -878,13 +887,13 @@ int faucet_session_get_junctions(faucet_session* s, faucet_junction_rec** recs_o
   if (!s->stitching) return fail(FAUCET_E_STATE, "no stitch has run in this session");
   int rc = stitch_finish(s);
   if (rc) return rc;
-  auto& r = s->recs_out;
+  const size_t nr = s->n_recs_out;
   if (recs_out) {
-    *recs_out = (faucet_junction_rec*)malloc(std::max<size_t>(1, r.size()) * sizeof(faucet_junction_rec));
+    *recs_out = (faucet_junction_rec*)malloc(std::max<size_t>(1, nr) * sizeof(faucet_junction_rec));
     if (!*recs_out) return fail(FAUCET_E_NOMEM, "malloc");
-    if (!r.empty()) memcpy(*recs_out, r.data(), r.size() * sizeof(faucet_junction_rec));
+    if (nr) memcpy(*recs_out, s->h_recs, nr * sizeof(faucet_junction_rec));
   }
-  if (n_out) *n_out = r.size();
+  if (n_out) *n_out = nr;
   if (stats) *stats = s->sstats;
   return 0;
 }
