@@ -38,6 +38,7 @@ struct Global {
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
   int stitch_impl = 1;    // 1: one warp per record (stitch.cuh, the faster one as measured); 2: one thread walks a record (stitch2.cuh)
   size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
+  bool scan_memo = true;              // scan_flags looks the extension masks of a k-mer up before it computes them (scan.cuh)
   bool retain_planes = false;         // pass 1 keeps the parsed planes of every batch in HBM for faucet_gpu_scan_retained
   size_t retain_budget = (size_t)64 << 30;
   unsigned long long ext_cap0 = 1ull << 24;
@@ -88,6 +89,9 @@ struct faucet_session {
   // pass 2 state
   uint32_t* d_bloom = nullptr;  // plain bloo2
   uint32_t* d_bloom1 = nullptr; // plain bloo1 (only materialised on request)
+  ulonglong2* d_memo = nullptr; // per-k-mer extension masks under the current bloo2 (scan_flags_memo_kernel)
+  uint64_t memo_entries = 0;
+  bool memo_dirty = true;       // bloo2 (or j) changed since the memo was last cleared
   uint8_t* d_flags = nullptr;
   // record table of the parsed batch (sequence line of record r = [seq_start[r], seq_end[r]))
   uint32_t *d_seq_start = nullptr, *d_seq_end = nullptr;
@@ -283,6 +287,8 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "stitch_impl") {
     if (value != 1 && value != 2) return fail(FAUCET_E_ARG, "stitch_impl must be 1 (warp per record) or 2 (thread per record)");
     g.stitch_impl = (int)value;
+  } else if (n == "scan_memo") {
+    g.scan_memo = value != 0;
   } else if (n == "retain_planes") {
     g.retain_planes = value != 0;
   } else if (n == "retain_budget") {
@@ -361,7 +367,7 @@ void faucet_session_destroy(faucet_session* s) {
   for (int i = 0; i < 3; i++) { cudaFree(s->d_textbufs[i]); if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]); }
   cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
-  cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom);
+  cudaFree(s->d_complex); cudaFree(s->d_fused); cudaFree(s->d_stamps); cudaFree(s->d_bloom); cudaFree(s->d_memo);
   retained_free(s);
   for (int i = 0; i < 3; i++) if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
   if (s->h_recs) cudaFreeHost(s->h_recs);
@@ -549,6 +555,7 @@ int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* blo
   CU(cudaMemsetAsync(&s->d_lctr->weight1, 0, 16, s->stream));
   bloom_split_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(s->d_fused, s->tai() / 32, bloo1_out ? s->d_bloom1 : nullptr,
                                                            s->d_bloom, s->d_lctr);
+  s->memo_dirty = true;
   s->launches++;
   if (bloo2_out) CU(cudaMemcpyAsync(bloo2_out, s->d_bloom, s->tai() / 8, cudaMemcpyDeviceToHost, s->stream));
   if (bloo1_out) CU(cudaMemcpyAsync(bloo1_out, s->d_bloom1, s->tai() / 8, cudaMemcpyDeviceToHost, s->stream));
@@ -567,6 +574,7 @@ int faucet_session_set_bloom(faucet_session* s, const uint8_t* bloo2) {
   int rc;
   if (!s->d_bloom && (rc = dmalloc(&s->d_bloom, s->tai() / 32))) return rc;
   CU(cudaMemcpyAsync(s->d_bloom, bloo2, s->tai() / 8, cudaMemcpyHostToDevice, s->stream));
+  s->memo_dirty = true;
   return 0;
 }
 
@@ -594,9 +602,30 @@ int faucet_session_scan_flags(faucet_session* s) {
   a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
   a.fplanes = s->impl == 2 ? reinterpret_cast<uint32_t*>(s->d_flags) : nullptr;
   const int grid = g.sm_count * SCAN_CTAS_PER_SM * 2;  // two full waves of resident CTAs
+  a.memo = nullptr; a.memo_mask = 0;
+  if (g.scan_memo) {
+    if (!s->d_memo) {  // sized from the filter (~ estimated k-mers): a cache, so a short table only costs recomputation
+      uint64_t want = std::max<uint64_t>(s->tai() / 2, (uint64_t)1 << 20);
+      want = std::min<uint64_t>(want, (uint64_t)1 << 29);
+      while (want >= ((uint64_t)1 << 20) && cudaMalloc((void**)&s->d_memo, want * sizeof(ulonglong2)) != cudaSuccess) {
+        cudaGetLastError();
+        s->d_memo = nullptr;
+        want >>= 1;
+      }
+      if (s->d_memo) { s->memo_entries = want; s->memo_dirty = true; }
+    }
+    if (s->d_memo) {
+      if (s->memo_dirty) {
+        CU(cudaMemsetAsync(s->d_memo, 0xff, s->memo_entries * sizeof(ulonglong2), s->stream));
+        s->memo_dirty = false;
+      }
+      a.memo = s->d_memo; a.memo_mask = s->memo_entries - 1;
+    }
+  }
   {
     KTimer kt(s, KT_SCAN);
-    DISPATCH_NH(scan_flags_kernel, s->n_hash, grid, SCAN_THREADS, s->stream, a);
+    if (a.memo) { DISPATCH_NH(scan_flags_memo_kernel, s->n_hash, grid, SCAN_THREADS, s->stream, a); }
+    else { DISPATCH_NH(scan_flags_kernel, s->n_hash, grid, SCAN_THREADS, s->stream, a); }
     s->launches++;
   }
   return check_launch("scan_flags");
@@ -994,6 +1023,7 @@ int faucet_session_prefix_or(faucet_session* s) {
 // puts a cross-process barrier before (all shards loaded and split) and after (all ranges written).
 int faucet_session_or_allreduce(faucet_session* s) {
   if (!s->peers_open) return fail(FAUCET_E_STATE, "peers not opened");
+  s->memo_dirty = true;  // every rank's bloo2 is rewritten (by its peers too)
   const uint64_t n_words = s->tai() / 32;
   if (n_words % 4) return fail(FAUCET_E_ARG, "Bloom filter too small for the multi-GPU reduce");
   PeerPtrs p{};
@@ -1083,6 +1113,7 @@ static int retained_push(faucet_session* s) {
 static int get_session(faucet_session** out, int k, int log2_tai, int n_hash, int j, int spacer) {
   faucet_session* c = g.cached;
   if (c && c->k == k && c->log2_tai == log2_tai && c->n_hash == n_hash && c->cap >= g.batch_bytes + TAIL_MAX) {
+    if (c->j != j) c->memo_dirty = true;  // the depth of the j-check is part of what the memo holds
     c->j = j; c->max_spacer = spacer;
     *out = c;
     return 0;

@@ -45,6 +45,8 @@ struct ScanArgs {
   const uint32_t* bloom;  // bloo2, plain reference layout viewed as little-endian u32 words
   uint32_t wmask;         // (tai - 1) >> 5: word index mask (log2_tai <= 37, checked by the session)
   int k, j, n_hash;
+  ulonglong2* memo;   // scan_flags_memo_kernel: {canonical k-mer, extension masks} per Bloom member seen so far
+  uint64_t memo_mask; // entries - 1 (power of two)
   uint8_t* flags;     // one byte per byte offset (warp-per-record stitch) ...
   uint32_t* fplanes;  // ... or, when not NULL, the same bits transposed: word w of plane i (= bit i) at fplanes[8 w + i]
 };
@@ -271,6 +273,226 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_ker
       if (lane < 8) a.fplanes[(size_t)w * 8 + lane] = mine;
     }
     __syncwarp();  // the queues are reused by the next word
+  }
+}
+
+// ---- the same flags, memoised per k-mer ---------------------------------------------------------------
+// Everything ReadScanner asks about a k-mer X that is in the filter -- which of its four forward
+// extensions are Bloom members and which of those pass the depth-j check, for X and for its reverse
+// complement -- is a pure function of (bloo2, X): 16 bits.  A read set covers every genome k-mer
+// `coverage` times, so those bits are computed once per DISTINCT k-mer and looked up afterwards:
+// one 16-byte probe of a table in HBM (key = canonical k-mer) instead of ~14 Bloom probes and ~11
+// evaluations of oldHash.  testForJunction for the FORWARD / BACKWARD half-step of a position is then
+// derived from the masks and the read's real neighbour bases, in the reference's nucleotide order.
+// The table is sized from the filter (it is a cache: when it is full, k-mers are simply recomputed),
+// holds only members (a k-mer that fails contains() has no flags), and must be cleared whenever bloo2
+// changes.  Entry: x = key, y = masks (bits 0-3 member / 4-7 j-check of the canonical form's
+// extensions, 8-11 / 12-15 of its reverse complement's), bit 63 of y set = not written yet.
+constexpr unsigned long long MEMO_EMPTY = ~0ull;
+constexpr int MEMO_PROBES = 8;
+constexpr int SCAN_QM = 256;  // 32 positions x 8 extensions
+
+struct ScanQueueM {  // per warp
+  unsigned long long canon[SCAN_QM];
+  unsigned long long h0[SCAN_QM];
+  uint8_t tag[SCAN_QM];
+  uint8_t res[SCAN_QM];
+  uint8_t cand[SCAN_QM];
+};
+
+// testForJunction (src/ReadScanner.cpp:36-56) from the masks of the half-step's base k-mer: bit 1 / 2 style result
+// {junction, number of alternates that were j-checked}
+__device__ __forceinline__ uint32_t junction_from_masks(uint32_t member, uint32_t jc, uint32_t real, bool have) {
+  if (!have) return 0u;
+  uint32_t cnt = 0, junc = 0;
+#pragma unroll
+  for (uint32_t nt = 0; nt < 4; nt++) {
+    if (nt == real || junc) continue;
+    if ((member >> nt) & 1u) { cnt++; junc = (jc >> nt) & 1u; }
+  }
+  return junc | (cnt << 1);
+}
+
+template <int NH>
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_memo_kernel(ScanArgs a) {
+  __shared__ ScanQueueM queues[SCAN_WARPS];
+  ScanQueueM& q = queues[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t warp = (blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * SCAN_THREADS) >> 5;
+  const int nh = NH ? NH : a.n_hash;
+  const int k = a.k;
+  const uint64_t kbits = k >= 32 ? 0xffffffffull : ((1ull << k) - 1ull);
+  const uint64_t mask = kmer_mask(k);
+  for (uint32_t w = warp; w < a.n_words; w += n_warps) {
+    const uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
+    const uint64_t win = inval_window(lo, hi, lane);
+    const bool start_ok = (win & kbits) == 0;
+    if (!__any_sync(0xffffffffu, start_ok)) {
+      if (a.fplanes && lane < 8) a.fplanes[(size_t)w * 8 + lane] = 0u;
+      continue;
+    }
+    const uint32_t p = (w << 5) + lane;
+    uint64_t fwd = 0, rc = 0, cn = 0;
+    bool is_c = true;       // the forward k-mer is the canonical form
+    uint32_t masks = 0;     // as stored: canonical form's in the low byte
+    bool have_masks = false, V = false;
+    uint64_t home = 0;
+    if (start_ok) {
+      fwd = kmer_at(a.packed, p, k);
+      rc = revcomp(fwd, k);
+      is_c = fwd <= rc;
+      cn = is_c ? fwd : rc;
+      // ---- memo lookup
+      home = (cn * 0x9E3779B97F4A7C15ull) >> 17;
+      home = (home ^ (home >> 23)) & a.memo_mask;
+      uint64_t h = home;
+#pragma unroll 1
+      for (int t = 0; t < MEMO_PROBES; t++) {
+        const ulonglong2 e = __ldcg(a.memo + h);
+        if (e.x == cn) {
+          if (!(e.y >> 63)) { masks = (uint32_t)e.y; have_masks = true; V = true; }
+          break;
+        }
+        if (e.x == MEMO_EMPTY) break;
+        h = (h + 1) & a.memo_mask;
+      }
+    }
+    const bool miss = start_ok && !have_masks;
+    if (__any_sync(0xffffffffu, miss)) {
+      // ---- the long way for the lanes that missed: V, then all 8 one-base extensions (4 of fwd, 4 of rc)
+      bool Vm = false;
+      if (miss) Vm = bloom_contains_all<NH>(a, fwd, rc);
+      uint32_t my_idx[2] = {0, 0};  // queue index of extension t, one byte each
+      uint32_t survived = 0;
+      int n1 = 0;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {  // four extensions at a time keeps the register budget of the plain kernel
+        uint64_t cq[4], hh[4];
+        uint32_t wd[4];
+        uint32_t cq_is_y = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const uint64_t y = ext_fwd(half ? rc : fwd, (uint32_t)c, mask), yr = ext_rc(half ? fwd : rc, (uint32_t)c, k);
+          cq_is_y |= (y < yr ? 1u : 0u) << c;
+          cq[c] = y < yr ? y : yr;
+          hh[c] = hash0(cq[c]);
+          wd[c] = (miss && Vm) ? bloom_word(a, hh[c]) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const bool hit = (wd[c] >> ((uint32_t)hh[c] & 31u)) & 1u;
+          const uint32_t b = __ballot_sync(0xffffffffu, hit);
+          if (hit) {
+            const int e = n1 + __popc(b & lt_mask);
+            q.canon[e] = cq[c]; q.h0[e] = hh[c]; q.tag[e] = (cq_is_y >> c) & 1u;
+            survived |= 1u << (4 * half + c);
+            my_idx[half] |= (uint32_t)e << (8 * c);
+          }
+          n1 += __popc(b);
+        }
+      }
+      __syncwarp();
+      int n2 = 0;
+      for (int base = 0; base < n1; base += 32) {  // remaining probes of the survivors
+        const int e = base + lane;
+        bool full = false;
+        if (e < n1) {
+          full = true;
+          if (nh > 1) {
+            const uint64_t h1 = hash1(q.canon[e]);
+            uint64_t h = q.h0[e];
+            uint32_t ok = 1u;
+#pragma unroll
+            for (int i = 1; i < (NH ? NH : MAX_NHASH); i++) {
+              if (i >= nh) break;
+              h += h1;
+              ok &= bloom_word(a, h) >> ((uint32_t)h & 31u);
+            }
+            full = ok & 1u;
+          }
+          q.res[e] = full ? (a.j == 0 ? 3 : 1) : 0;
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, full);
+        if (full) q.cand[n2 + __popc(b & lt_mask)] = (uint8_t)e;
+        n2 += __popc(b);
+      }
+      __syncwarp();
+      if (a.j == 1) {  // depth-j check of the members (JChecker::jcheck)
+        for (int base = 0; base < 4 * n2; base += 32) {
+          const int task = base + lane;
+          if (task < 4 * n2) {
+            const int e = q.cand[task >> 2];
+            const uint32_t c = task & 3;
+            const uint64_t cc = q.canon[e], cr = revcomp(cc, k);
+            const bool is_y = q.tag[e] & 1;
+            const uint64_t y = is_y ? cc : cr, yr = is_y ? cr : cc;
+            if (bloom_contains<NH>(a, ext_fwd(y, c, mask), ext_rc(yr, c, k))) q.res[e] = 3;
+          }
+        }
+      } else if (a.j > 1) {
+        for (int base = 0; base < n2; base += 32) {
+          const int ci = base + lane;
+          if (ci < n2) {
+            const int e = q.cand[ci];
+            const uint64_t cc = q.canon[e], cr = revcomp(cc, k);
+            const bool is_y = q.tag[e] & 1;
+            if (jcheck<NH>(a, is_y ? cc : cr, is_y ? cr : cc, mask)) q.res[e] = 3;
+          }
+        }
+      }
+      __syncwarp();
+      if (miss) {
+        V = Vm;
+        if (Vm) {
+          uint32_t mf = 0, mb = 0;  // {member nibble, j-check nibble} of fwd's and of rc's extensions
+#pragma unroll
+          for (int t = 0; t < 8; t++)
+            if ((survived >> t) & 1u) {
+              const uint32_t r = q.res[(my_idx[t >> 2] >> (8 * (t & 3))) & 0xffu];
+              const uint32_t bits = (r & 1u) | ((r >> 1) & 1u) << 4;
+              if (t < 4) mf |= bits << t; else mb |= bits << (t - 4);
+            }
+          masks = is_c ? (mf | (mb << 8)) : (mb | (mf << 8));
+          have_masks = true;
+          // publish (a cache: give up quietly when the neighbourhood is full or somebody else was first)
+          uint64_t h = home;
+#pragma unroll 1
+          for (int t = 0; t < MEMO_PROBES; t++) {
+            const unsigned long long old = atomicCAS(&a.memo[h].x, MEMO_EMPTY, (unsigned long long)cn);
+            if (old == MEMO_EMPTY) { __stcg(&a.memo[h].y, (unsigned long long)masks); break; }
+            if (old == cn) break;
+            h = (h + 1) & a.memo_mask;
+          }
+        }
+      }
+      __syncwarp();  // the queues are reused by the next word
+    }
+    // ---- flags from the masks and the read's real neighbours
+    uint32_t f = 0;
+    if (start_ok && V) {
+      const uint32_t mf = is_c ? (masks & 0xffu) : ((masks >> 8) & 0xffu), mb = is_c ? ((masks >> 8) & 0xffu) : (masks & 0xffu);
+      // FORWARD half-step needs read[p+k]; BACKWARD needs read[p-1] (utils/ReadKmer.cpp:107-114)
+      const bool has_next = !((win >> k) & 1ull);
+      const bool has_prev = lane ? !((lo >> (lane - 1)) & 1u) : (w && !(__ldg(a.inval + w - 1) >> 31));
+      const uint32_t real_f = has_next ? code_at(a.packed, p + k) : 0u;
+      const uint32_t real_b = has_prev ? nt_comp(code_at(a.packed, p - 1)) : 0u;
+      const uint32_t jf = junction_from_masks(mf & 15u, mf >> 4, real_f, has_next);
+      const uint32_t jb = junction_from_masks(mb & 15u, mb >> 4, real_b, has_prev);
+      f = 1u | ((jf & 1u) << 1) | ((jb & 1u) << 2) | ((jf >> 1) << 3) | ((jb >> 1) << 5);
+    }
+    if (a.fplanes) {
+      uint32_t mine = 0;
+#pragma unroll
+      for (int i = 0; i < 7; i++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (f >> i) & 1u);
+        if (lane == i) mine = b;
+      }
+      if (lane < 8) a.fplanes[(size_t)w * 8 + lane] = mine;
+    } else if (start_ok) {
+      a.flags[p] = (uint8_t)f;
+    }
   }
 }
 

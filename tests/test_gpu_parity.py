@@ -345,3 +345,24 @@ def test_path_entry_points_stream_the_file(fb, oracle, small_fq, tmp_path):
             assert gsst == osst and _strip(grecs) == _strip(orecs)
     finally:
         fb.set_batch_bytes(256 << 20)
+
+
+@pytest.mark.parametrize("j", [0, 1, 2])
+def test_scan_flags_memo_is_invisible(fb, oracle, small_fq, j):
+    """scan_flags looks up the per-k-mer extension masks it has already computed (scan_memo, the default) or
+    computes every position from the Bloom filter (scan_memo = 0): same junction map, same counters; and a memo
+    that is far too small for the input (it is a cache) changes nothing either"""
+    _, text = small_fq
+    k = 31
+    lt, nh = _geom(oracle, 100000, 50000)
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    orecs, ost = oracle.scan(text, True, True, 1, k, j, 100, b2, lt, nh)
+    try:
+        for memo in (0, 1):
+            fb.set_tuning("scan_memo", memo)
+            fb.set_batch_bytes(500_000)  # several batches share one memo
+            grecs, gst = fb.scan_mem(text, True, True, 1, k, j, 100, b2, lt, nh)
+            assert gst == ost and _strip(grecs) == _strip(orecs), memo
+    finally:
+        fb.set_tuning("scan_memo", 1)
+        fb.set_batch_bytes(256 << 20)
