@@ -38,6 +38,7 @@ struct Global {
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
   int stitch_impl = 1;    // 1: one warp per record (stitch.cuh, the faster one as measured); 2: one thread walks a record (stitch2.cuh)
   size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
+  int memo_shift = 1;                 // memo entries = Bloom bits >> memo_shift (8 bytes each): load <= ~0.3 of the 8-probe cache
   bool scan_memo = true;              // scan_flags looks the extension masks of a k-mer up before it computes them (scan.cuh)
   bool retain_planes = false;         // pass 1 keeps the parsed planes of every batch in HBM for faucet_gpu_scan_retained
   size_t retain_budget = (size_t)64 << 30;
@@ -89,7 +90,7 @@ struct faucet_session {
   // pass 2 state
   uint32_t* d_bloom = nullptr;  // plain bloo2
   uint32_t* d_bloom1 = nullptr; // plain bloo1 (only materialised on request)
-  ulonglong2* d_memo = nullptr; // per-k-mer extension masks under the current bloo2 (scan_flags_memo_kernel)
+  unsigned long long* d_memo = nullptr;  // per-k-mer extension masks under the current bloo2 (scan_flags_memo_kernel)
   uint64_t memo_entries = 0;
   bool memo_dirty = true;       // bloo2 (or j) changed since the memo was last cleared
   uint8_t* d_flags = nullptr;
@@ -289,6 +290,9 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
     g.stitch_impl = (int)value;
   } else if (n == "scan_memo") {
     g.scan_memo = value != 0;
+  } else if (n == "memo_shift") {
+    if (value > 16) return fail(FAUCET_E_ARG, "memo_shift out of range");
+    g.memo_shift = (int)value;
   } else if (n == "retain_planes") {
     g.retain_planes = value != 0;
   } else if (n == "retain_budget") {
@@ -605,9 +609,9 @@ int faucet_session_scan_flags(faucet_session* s) {
   a.memo = nullptr; a.memo_mask = 0;
   if (g.scan_memo) {
     if (!s->d_memo) {  // sized from the filter (~ estimated k-mers): a cache, so a short table only costs recomputation
-      uint64_t want = std::max<uint64_t>(s->tai() / 2, (uint64_t)1 << 20);
-      want = std::min<uint64_t>(want, (uint64_t)1 << 29);
-      while (want >= ((uint64_t)1 << 20) && cudaMalloc((void**)&s->d_memo, want * sizeof(ulonglong2)) != cudaSuccess) {
+      uint64_t want = std::max<uint64_t>(s->tai() >> g.memo_shift, (uint64_t)1 << 20);
+      want = std::min<uint64_t>(want, (uint64_t)1 << 30);
+      while (want >= ((uint64_t)1 << 20) && cudaMalloc((void**)&s->d_memo, want * 8) != cudaSuccess) {
         cudaGetLastError();
         s->d_memo = nullptr;
         want >>= 1;
@@ -616,10 +620,12 @@ int faucet_session_scan_flags(faucet_session* s) {
     }
     if (s->d_memo) {
       if (s->memo_dirty) {
-        CU(cudaMemsetAsync(s->d_memo, 0xff, s->memo_entries * sizeof(ulonglong2), s->stream));
+        CU(cudaMemsetAsync(s->d_memo, 0xff, s->memo_entries * 8, s->stream));
         s->memo_dirty = false;
       }
-      a.memo = s->d_memo; a.memo_mask = s->memo_entries - 1;
+      int lg = 0;
+      while (((uint64_t)1 << lg) < s->memo_entries) lg++;
+      a.memo = s->d_memo; a.memo_mask = s->memo_entries - 1; a.memo_qbits = 64 - lg;
     }
   }
   {

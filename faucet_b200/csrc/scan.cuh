@@ -45,8 +45,9 @@ struct ScanArgs {
   const uint32_t* bloom;  // bloo2, plain reference layout viewed as little-endian u32 words
   uint32_t wmask;         // (tai - 1) >> 5: word index mask (log2_tai <= 37, checked by the session)
   int k, j, n_hash;
-  ulonglong2* memo;   // scan_flags_memo_kernel: {canonical k-mer, extension masks} per Bloom member seen so far
-  uint64_t memo_mask; // entries - 1 (power of two)
+  unsigned long long* memo;  // scan_flags_memo_kernel: one word per Bloom member seen so far (see there)
+  uint64_t memo_mask;        // entries - 1 (power of two, >= 2^20)
+  int memo_qbits;            // 64 - log2(entries): bits of the hash kept in the entry
   uint8_t* flags;     // one byte per byte offset (warp-per-record stitch) ...
   uint32_t* fplanes;  // ... or, when not NULL, the same bits transposed: word w of plane i (= bit i) at fplanes[8 w + i]
 };
@@ -284,10 +285,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_ker
 // one 16-byte probe of a table in HBM (key = canonical k-mer) instead of ~14 Bloom probes and ~11
 // evaluations of oldHash.  testForJunction for the FORWARD / BACKWARD half-step of a position is then
 // derived from the masks and the read's real neighbour bases, in the reference's nucleotide order.
-// The table is sized from the filter (it is a cache: when it is full, k-mers are simply recomputed),
-// holds only members (a k-mer that fails contains() has no flags), and must be cleared whenever bloo2
-// changes.  Entry: x = key, y = masks (bits 0-3 member / 4-7 j-check of the canonical form's
-// extensions, 8-11 / 12-15 of its reverse complement's), bit 63 of y set = not written yet.
+// The table is sized from the filter (it is a cache: when a neighbourhood is full, the k-mer is simply
+// recomputed), holds only members (a k-mer that fails contains() has no flags), and must be cleared
+// whenever bloo2 changes.  One 8-byte word per k-mer, so that the table of an E. coli-sized input
+// (64 MB) stays in L2: the canonical k-mer goes through a BIJECTIVE 64-bit mix; the top log2(entries)
+// bits pick the home slot and the rest (<= 44 bits) is stored next to the probe displacement, so the
+// word identifies the k-mer exactly:  [0 | disp:3 | quotient:44 | masks:16], all ones = empty.
+// masks: bits 0-3 member / 4-7 j-check of the canonical form's extensions, 8-11 / 12-15 of its reverse
+// complement's.  One word = one atomicCAS to publish, no torn reads.
 constexpr unsigned long long MEMO_EMPTY = ~0ull;
 constexpr int MEMO_PROBES = 8;
 constexpr int SCAN_QM = 256;  // 32 positions x 8 extensions
@@ -326,37 +331,42 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
   const uint64_t kbits = k >= 32 ? 0xffffffffull : ((1ull << k) - 1ull);
   const uint64_t mask = kmer_mask(k);
   for (uint32_t w = warp; w < a.n_words; w += n_warps) {
+    // everything the hit path reads from the planes is requested up front and in parallel (the validity words, the
+    // k-mer's three code words, the neighbour bases): the dependent chain is planes -> memo probe -> flags
+    const uint32_t p = (w << 5) + lane;
     const uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
+    const uint32_t prev_word = w ? __ldg(a.inval + w - 1) : 0xffffffffu;
+    const uint64_t fwd_raw = kmer_at(a.packed, p, k);
+    const uint32_t next_code = code_at(a.packed, p + k);
+    const uint32_t prev_code = p ? code_at(a.packed, p - 1) : 0u;
     const uint64_t win = inval_window(lo, hi, lane);
     const bool start_ok = (win & kbits) == 0;
     if (!__any_sync(0xffffffffu, start_ok)) {
       if (a.fplanes && lane < 8) a.fplanes[(size_t)w * 8 + lane] = 0u;
       continue;
     }
-    const uint32_t p = (w << 5) + lane;
     uint64_t fwd = 0, rc = 0, cn = 0;
     bool is_c = true;       // the forward k-mer is the canonical form
     uint32_t masks = 0;     // as stored: canonical form's in the low byte
     bool have_masks = false, V = false;
-    uint64_t home = 0;
+    uint64_t home = 0, quot = 0;
     if (start_ok) {
-      fwd = kmer_at(a.packed, p, k);
+      fwd = fwd_raw;
       rc = revcomp(fwd, k);
       is_c = fwd <= rc;
       cn = is_c ? fwd : rc;
       // ---- memo lookup
-      home = (cn * 0x9E3779B97F4A7C15ull) >> 17;
-      home = (home ^ (home >> 23)) & a.memo_mask;
-      uint64_t h = home;
+      uint64_t h = cn * 0x9E3779B97F4A7C15ull;  // odd multiplier, xor-shift by half: both bijections
+      h ^= h >> 32;
+      h *= 0xD6E8FEB86659FD93ull;
+      h ^= h >> 32;
+      home = h >> a.memo_qbits;
+      quot = h & ((1ull << a.memo_qbits) - 1ull);
 #pragma unroll 1
-      for (int t = 0; t < MEMO_PROBES; t++) {
-        const ulonglong2 e = __ldcg(a.memo + h);
-        if (e.x == cn) {
-          if (!(e.y >> 63)) { masks = (uint32_t)e.y; have_masks = true; V = true; }
-          break;
-        }
-        if (e.x == MEMO_EMPTY) break;
-        h = (h + 1) & a.memo_mask;
+      for (uint64_t t = 0; t < MEMO_PROBES; t++) {
+        const unsigned long long e = __ldcg(a.memo + ((home + t) & a.memo_mask));
+        if (e == MEMO_EMPTY) break;
+        if ((e >> 16) == ((t << 44) | quot)) { masks = (uint32_t)(e & 0xffffu); have_masks = true; V = true; break; }
       }
     }
     const bool miss = start_ok && !have_masks;
@@ -457,13 +467,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
           masks = is_c ? (mf | (mb << 8)) : (mb | (mf << 8));
           have_masks = true;
           // publish (a cache: give up quietly when the neighbourhood is full or somebody else was first)
-          uint64_t h = home;
 #pragma unroll 1
-          for (int t = 0; t < MEMO_PROBES; t++) {
-            const unsigned long long old = atomicCAS(&a.memo[h].x, MEMO_EMPTY, (unsigned long long)cn);
-            if (old == MEMO_EMPTY) { __stcg(&a.memo[h].y, (unsigned long long)masks); break; }
-            if (old == cn) break;
-            h = (h + 1) & a.memo_mask;
+          for (uint64_t t = 0; t < MEMO_PROBES; t++) {
+            const unsigned long long word = (((t << 44) | quot) << 16) | masks;
+            const unsigned long long old = atomicCAS(a.memo + ((home + t) & a.memo_mask), MEMO_EMPTY, word);
+            if (old == MEMO_EMPTY || (old >> 16) == (word >> 16)) break;
           }
         }
       }
@@ -475,9 +483,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
       const uint32_t mf = is_c ? (masks & 0xffu) : ((masks >> 8) & 0xffu), mb = is_c ? ((masks >> 8) & 0xffu) : (masks & 0xffu);
       // FORWARD half-step needs read[p+k]; BACKWARD needs read[p-1] (utils/ReadKmer.cpp:107-114)
       const bool has_next = !((win >> k) & 1ull);
-      const bool has_prev = lane ? !((lo >> (lane - 1)) & 1u) : (w && !(__ldg(a.inval + w - 1) >> 31));
-      const uint32_t real_f = has_next ? code_at(a.packed, p + k) : 0u;
-      const uint32_t real_b = has_prev ? nt_comp(code_at(a.packed, p - 1)) : 0u;
+      const bool has_prev = lane ? !((lo >> (lane - 1)) & 1u) : !(prev_word >> 31);
+      const uint32_t real_f = has_next ? next_code : 0u;
+      const uint32_t real_b = has_prev ? nt_comp(prev_code) : 0u;
       const uint32_t jf = junction_from_masks(mf & 15u, mf >> 4, real_f, has_next);
       const uint32_t jb = junction_from_masks(mb & 15u, mb >> 4, real_b, has_prev);
       f = 1u | ((jf & 1u) << 1) | ((jb & 1u) << 2) | ((jf >> 1) << 3) | ((jb >> 1) << 5);
