@@ -606,7 +606,13 @@ int faucet_session_scan_flags(faucet_session* s) {
   a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
   a.fplanes = s->impl == 2 ? reinterpret_cast<uint32_t*>(s->d_flags) : nullptr;
   const int grid = g.sm_count * SCAN_CTAS_PER_SM * 2;  // two full waves of resident CTAs
-  a.memo = nullptr; a.memo_mask = 0;
+  a.memo = nullptr; a.memo_mask = 0; a.dbg = nullptr;
+  static unsigned long long* d_dbg = nullptr;
+  if (getenv("FAUCET_SCAN_DEBUG")) {
+    if (!d_dbg) { cudaMalloc((void**)&d_dbg, 64); }
+    cudaMemsetAsync(d_dbg, 0, 64, s->stream);
+    a.dbg = d_dbg;
+  }
   if (g.scan_memo) {
     if (!s->d_memo) {  // sized from the filter (~ estimated k-mers): a cache, so a short table only costs recomputation
       uint64_t want = std::max<uint64_t>(s->tai() >> g.memo_shift, (uint64_t)1 << 20);
@@ -633,6 +639,12 @@ int faucet_session_scan_flags(faucet_session* s) {
     if (a.memo) { DISPATCH_NH(scan_flags_memo_kernel, s->n_hash, grid, SCAN_THREADS, s->stream, a); }
     else { DISPATCH_NH(scan_flags_kernel, s->n_hash, grid, SCAN_THREADS, s->stream, a); }
     s->launches++;
+  }
+  if (a.dbg) {
+    unsigned long long h[3];
+    cudaStreamSynchronize(s->stream);
+    cudaMemcpy(h, a.dbg, 24, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "scan_flags debug: %llu lanes missed, %llu warp passes through the long path, %llu failed inserts\n", h[0], h[1], h[2]);
   }
   return check_launch("scan_flags");
 }

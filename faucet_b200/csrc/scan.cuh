@@ -48,6 +48,7 @@ struct ScanArgs {
   unsigned long long* memo;  // scan_flags_memo_kernel: one word per Bloom member seen so far (see there)
   uint64_t memo_mask;        // entries - 1 (power of two, >= 2^20)
   int memo_qbits;            // 64 - log2(entries): bits of the hash kept in the entry
+  unsigned long long* dbg;   // optional counters: [0] lanes that missed, [1] warp passes through the long path, [2] failed inserts
   uint8_t* flags;     // one byte per byte offset (warp-per-record stitch) ...
   uint32_t* fplanes;  // ... or, when not NULL, the same bits transposed: word w of plane i (= bit i) at fplanes[8 w + i]
 };
@@ -321,6 +322,10 @@ __device__ __forceinline__ uint32_t junction_from_masks(uint32_t member, uint32_
 template <int NH>
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_memo_kernel(ScanArgs a) {
   __shared__ ScanQueueM queues[SCAN_WARPS];
+  __shared__ uint8_t jlut[1024];  // junction_from_masks for every (member, j-check, real nucleotide)
+  for (int i = threadIdx.x; i < 1024; i += SCAN_THREADS)
+    jlut[i] = (uint8_t)junction_from_masks((uint32_t)i & 15u, ((uint32_t)i >> 4) & 15u, (uint32_t)i >> 8, true);
+  __syncthreads();
   ScanQueueM& q = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -356,10 +361,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
       is_c = fwd <= rc;
       cn = is_c ? fwd : rc;
       // ---- memo lookup
-      uint64_t h = cn * 0x9E3779B97F4A7C15ull;  // odd multiplier, xor-shift by half: both bijections
-      h ^= h >> 32;
-      h *= 0xD6E8FEB86659FD93ull;
-      h ^= h >> 32;
+      uint64_t h = cn * 0x9E3779B97F4A7C15ull;  // odd multiplier, xor-shift: both bijections; the top bits of the
+      h ^= h >> 29;                             // product (the home slot) depend on every bit of the k-mer
       home = h >> a.memo_qbits;
       quot = h & ((1ull << a.memo_qbits) - 1ull);
 #pragma unroll 1
@@ -371,6 +374,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
     }
     const bool miss = start_ok && !have_masks;
     if (__any_sync(0xffffffffu, miss)) {
+      if (a.dbg) {
+        const uint32_t mm = __ballot_sync(0xffffffffu, miss);
+        if (lane == 0) { atomicAdd(a.dbg, (unsigned long long)__popc(mm)); atomicAdd(a.dbg + 1, 1ull); }
+      }
       // ---- the long way for the lanes that missed: V, then all 8 one-base extensions (4 of fwd, 4 of rc)
       bool Vm = false;
       if (miss) Vm = bloom_contains_all<NH>(a, fwd, rc);
@@ -472,6 +479,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
             const unsigned long long word = (((t << 44) | quot) << 16) | masks;
             const unsigned long long old = atomicCAS(a.memo + ((home + t) & a.memo_mask), MEMO_EMPTY, word);
             if (old == MEMO_EMPTY || (old >> 16) == (word >> 16)) break;
+            if (a.dbg && t == MEMO_PROBES - 1) atomicAdd(a.dbg + 2, 1ull);
           }
         }
       }
@@ -486,8 +494,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
       const bool has_prev = lane ? !((lo >> (lane - 1)) & 1u) : !(prev_word >> 31);
       const uint32_t real_f = has_next ? next_code : 0u;
       const uint32_t real_b = has_prev ? nt_comp(prev_code) : 0u;
-      const uint32_t jf = junction_from_masks(mf & 15u, mf >> 4, real_f, has_next);
-      const uint32_t jb = junction_from_masks(mb & 15u, mb >> 4, real_b, has_prev);
+      const uint32_t jf = has_next ? jlut[mf | (real_f << 8)] : 0u;
+      const uint32_t jb = has_prev ? jlut[mb | (real_b << 8)] : 0u;
       f = 1u | ((jf & 1u) << 1) | ((jb & 1u) << 2) | ((jf >> 1) << 3) | ((jb >> 1) << 5);
     }
     if (a.fplanes) {
