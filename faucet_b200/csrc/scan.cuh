@@ -335,21 +335,29 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
   const int k = a.k;
   const uint64_t kbits = k >= 32 ? 0xffffffffull : ((1ull << k) - 1ull);
   const uint64_t mask = kmer_mask(k);
+  // The validity words of the NEXT word of text are fetched one iteration ahead, so a word without any k-mer start
+  // (header and quality lines: ~60 % of a FASTQ) is dismissed without touching the code plane, and for the others the
+  // k-mer's code words and the neighbour bases are requested together: planes -> memo probe -> flags.
+  uint32_t lo_n = 0xffffffffu, hi_n = 0xffffffffu, prev_n = 0xffffffffu;
+  if (warp < a.n_words) {
+    lo_n = __ldg(a.inval + warp); hi_n = __ldg(a.inval + warp + 1);
+    if (warp) prev_n = __ldg(a.inval + warp - 1);
+  }
   for (uint32_t w = warp; w < a.n_words; w += n_warps) {
-    // everything the hit path reads from the planes is requested up front and in parallel (the validity words, the
-    // k-mer's three code words, the neighbour bases): the dependent chain is planes -> memo probe -> flags
     const uint32_t p = (w << 5) + lane;
-    const uint32_t lo = __ldg(a.inval + w), hi = __ldg(a.inval + w + 1);
-    const uint32_t prev_word = w ? __ldg(a.inval + w - 1) : 0xffffffffu;
-    const uint64_t fwd_raw = kmer_at(a.packed, p, k);
-    const uint32_t next_code = code_at(a.packed, p + k);
-    const uint32_t prev_code = p ? code_at(a.packed, p - 1) : 0u;
+    const uint32_t lo = lo_n, hi = hi_n, prev_word = prev_n;
+    if (w + n_warps < a.n_words) {
+      lo_n = __ldg(a.inval + w + n_warps); hi_n = __ldg(a.inval + w + n_warps + 1); prev_n = __ldg(a.inval + w + n_warps - 1);
+    }
     const uint64_t win = inval_window(lo, hi, lane);
     const bool start_ok = (win & kbits) == 0;
     if (!__any_sync(0xffffffffu, start_ok)) {
       if (a.fplanes && lane < 8) a.fplanes[(size_t)w * 8 + lane] = 0u;
       continue;
     }
+    const uint64_t fwd_raw = kmer_at(a.packed, p, k);
+    const uint32_t next_code = code_at(a.packed, p + k);
+    const uint32_t prev_code = p ? code_at(a.packed, p - 1) : 0u;
     uint64_t fwd = 0, rc = 0, cn = 0;
     bool is_c = true;       // the forward k-mer is the canonical form
     uint32_t masks = 0;     // as stored: canonical form's in the low byte
