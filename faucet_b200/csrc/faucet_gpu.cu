@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -93,6 +94,7 @@ struct faucet_session {
   unsigned long long* d_memo = nullptr;  // per-k-mer extension masks under the current bloo2 (scan_flags_memo_kernel)
   uint64_t memo_entries = 0;
   bool memo_dirty = true;       // bloo2 (or j) changed since the memo was last cleared
+  int memo_kind = 0;            // what the table holds: 1 = pass 1's saturated k-mers, 2 = pass 2's extension masks
   uint8_t* d_flags = nullptr;
   // record table of the parsed batch (sequence line of record r = [seq_start[r], seq_end[r]))
   uint32_t *d_seq_start = nullptr, *d_seq_end = nullptr;
@@ -362,6 +364,7 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
 }
 
 static void retained_free(faucet_session* s);
+static int memo_acquire(faucet_session* s, int kind, int* qbits);
 
 void faucet_session_destroy(faucet_session* s) {
   if (!s) return;
@@ -514,6 +517,7 @@ int faucet_session_load(faucet_session* s) {
   a.fused = s->d_fused; a.stamps = s->d_stamps; a.tai_mask = s->tai() - 1; a.base = s->stamp_base;
   a.k = s->k; a.n_hash = s->n_hash; a.ctr = s->d_lctr; a.text = s->d_text; a.complex_list = s->d_complex;
   a.n_complex = s->h_pctr.n_complex;
+
   // Sub-batches: kernel A treats "all bits already in bloo1 when the sub-batch starts" as contained and
   // only the rest touches the 4-byte-per-bit stamp array, so short early sub-batches (bloo1 fills
   // fast) keep almost every k-mer of a deep-coverage stream off the stamps.  Any partition by start
@@ -597,6 +601,32 @@ int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_
   return 0;
 }
 
+// The k-mer cache of scan.cuh (kind 2; a pass-1 cache of saturated k-mers, kind 1, was tried and is slower than the
+// three probes of the L2-resident fused filter it replaces).  Cleared when what it caches went stale.  Sized from the filter (~ estimated k-mers); a cache, so a
+// short table only costs recomputation.
+static int memo_acquire(faucet_session* s, int kind, int* qbits) {
+  if (!s->d_memo) {
+    uint64_t want = std::max<uint64_t>(s->tai() >> g.memo_shift, (uint64_t)1 << 20);
+    want = std::min<uint64_t>(want, (uint64_t)1 << 30);
+    while (want >= ((uint64_t)1 << 20) && cudaMalloc((void**)&s->d_memo, want * 8) != cudaSuccess) {
+      cudaGetLastError();
+      s->d_memo = nullptr;
+      want >>= 1;
+    }
+    if (s->d_memo) { s->memo_entries = want; s->memo_dirty = true; }
+  }
+  if (!s->d_memo) return 0;
+  if (s->memo_dirty || s->memo_kind != kind) {
+    CU(cudaMemsetAsync(s->d_memo, 0xff, s->memo_entries * 8, s->stream));
+    s->memo_dirty = false;
+    s->memo_kind = kind;
+  }
+  int lg = 0;
+  while (((uint64_t)1 << lg) < s->memo_entries) lg++;
+  *qbits = 64 - lg;
+  return 0;
+}
+
 int faucet_session_scan_flags(faucet_session* s) {
   if (!s->parsed) return fail(FAUCET_E_STATE, "faucet_session_scan_flags before faucet_session_parse");
   int rc = ensure_scan_buffers(s);
@@ -614,25 +644,9 @@ int faucet_session_scan_flags(faucet_session* s) {
     a.dbg = d_dbg;
   }
   if (g.scan_memo) {
-    if (!s->d_memo) {  // sized from the filter (~ estimated k-mers): a cache, so a short table only costs recomputation
-      uint64_t want = std::max<uint64_t>(s->tai() >> g.memo_shift, (uint64_t)1 << 20);
-      want = std::min<uint64_t>(want, (uint64_t)1 << 30);
-      while (want >= ((uint64_t)1 << 20) && cudaMalloc((void**)&s->d_memo, want * 8) != cudaSuccess) {
-        cudaGetLastError();
-        s->d_memo = nullptr;
-        want >>= 1;
-      }
-      if (s->d_memo) { s->memo_entries = want; s->memo_dirty = true; }
-    }
-    if (s->d_memo) {
-      if (s->memo_dirty) {
-        CU(cudaMemsetAsync(s->d_memo, 0xff, s->memo_entries * 8, s->stream));
-        s->memo_dirty = false;
-      }
-      int lg = 0;
-      while (((uint64_t)1 << lg) < s->memo_entries) lg++;
-      a.memo = s->d_memo; a.memo_mask = s->memo_entries - 1; a.memo_qbits = 64 - lg;
-    }
+    int qb = 0;
+    if ((rc = memo_acquire(s, 2, &qb))) return rc;
+    if (s->d_memo) { a.memo = s->d_memo; a.memo_mask = s->memo_entries - 1; a.memo_qbits = qb; }
   }
   {
     KTimer kt(s, KT_SCAN);
@@ -1411,16 +1425,24 @@ int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int
                                         lpf_log2_tai, lpf_n_hash)))
     return rc;
   uint32_t *inval = s->d_inval, *packed = s->d_packed, *ss = s->d_seq_start, *se = s->d_seq_end;
+  const bool trace = getenv("FAUCET_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
   for (auto& b : s->retained) {  // the session's plane pointers visit the retained batches in stream order
     s->d_inval = b.inval; s->d_packed = b.packed; s->d_seq_start = b.seq_start; s->d_seq_end = b.seq_end;
     s->n = b.n; s->n_recs = b.n_recs; s->fastq = b.fastq; s->parsed = true;
+    const double t0 = now();
     if ((rc = faucet_session_scan_flags(s)) || (rc = faucet_session_stitch_batch(s))) break;
+    if (trace) fprintf(stderr, "scan_retained: batch of %zu bytes, %u records: %.2f ms\n", b.n, b.n_recs, now() - t0);
   }
+  if (trace) fprintf(stderr, "scan_retained: %zu batches %.2f ms\n", s->retained.size(), now() - t_begin);
   s->d_inval = inval; s->d_packed = packed; s->d_seq_start = ss; s->d_seq_end = se;
   s->parsed = false;
   if (rc) return rc;
+  const double t_collect = now();
   rc = faucet_session_get_junctions(s, recs_out, n_recs_out, stats);
   drain_events(s);
+  if (trace) fprintf(stderr, "scan_retained: collect %.2f ms\n", now() - t_collect);
   return rc;
 }
 
