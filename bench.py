@@ -351,6 +351,8 @@ def run_ours(args, w):
         per_launch_ms = kernel_ms[dom][0] / max(1, kernel_ms[dom][1])
         a_dom = a_scan if dom == "scan_flags" else a_load
         achieved = kmers_per_pass * a_dom / (per_launch_ms * 1e-3) / 1e9
+        text_per_kmer = n_text / max(1, kmers_per_pass)
+        own_bytes = (8.0 + text_per_kmer * (0.375 + 1.0)) if dom == "scan_flags" else a_dom
         out = {
             "metric": "k-mers/sec (Bloom load + junction scan)", "value": kmers_all * args.steps / (ms_all * 1e-3),
             "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -373,7 +375,13 @@ def run_ours(args, w):
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom), "peak_kind": peak_kind,
-                         "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms},
+                         "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms,
+                         # SURVEY 8(d)'s sector model = the bytes the REFERENCE's algorithm moves per k-mer.  The memoised
+                         # scan_flags looks the 16 result bits of a k-mer up instead of re-deriving them, so it moves far
+                         # fewer (`traffic`): frac > 1 means work avoided, not bandwidth exceeded.  `own_*`: what this
+                         # kernel itself has to move (8-byte memo word + planes in + flags out per k-mer start).
+                         "own_bytes_per_kmer": own_bytes, "own_achieved": kmers_per_pass * own_bytes / (per_launch_ms * 1e-3) / 1e9,
+                         "own_frac": kmers_per_pass * own_bytes / (per_launch_ms * 1e-3) / 1e9 / peak},
             "kernels_ms_per_step": {n: v[0] / args.steps for n, v in kernel_ms.items()},
             "bloom_weight2": weight2, "contained_fraction": r_contained, "stitch": stitch_info,
         }
