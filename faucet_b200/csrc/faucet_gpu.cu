@@ -1274,9 +1274,13 @@ static int for_each_batch(faucet_session* s, TextSource& src, bool fastq, uint64
   const size_t room = s->cap - TAIL_MAX - 64;
   std::vector<std::pair<size_t, size_t>> chunks;  // (offset, length) in the text
   {
-    size_t ramp = std::min(room, (size_t)32 << 20), off = 0;
+    // ramp up from 32 MiB (the first copy overlaps nothing) and down again at the end (the kernels of the last batch
+    // run after the last copy: keep that batch small)
+    const size_t small = std::min(room, (size_t)32 << 20);
+    size_t ramp = small, off = 0;
     do {
-      const size_t len = std::min(ramp, n - off);
+      const size_t rest = n - off;
+      const size_t len = rest <= small ? rest : std::min(ramp, std::max(rest / 2, small));
       chunks.push_back({off, len});
       off += len;
       ramp = std::min(room, ramp * 2);
