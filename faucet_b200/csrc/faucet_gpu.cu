@@ -39,6 +39,7 @@ struct Global {
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
   int stitch_impl = 1;    // 1: one warp per record (stitch.cuh, the faster one as measured); 2: one thread walks a record (stitch2.cuh)
   size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
+  int load_memo_log2 = 29;            // pass 1 caches saturated k-mers when the filter has at least 2^this bits
   int memo_shift = 1;                 // memo entries = Bloom bits >> memo_shift (8 bytes each): load <= ~0.3 of the 8-probe cache
   bool scan_memo = true;              // scan_flags looks the extension masks of a k-mer up before it computes them (scan.cuh)
   bool retain_planes = false;         // pass 1 keeps the parsed planes of every batch in HBM for faucet_gpu_scan_retained
@@ -292,6 +293,8 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
     g.stitch_impl = (int)value;
   } else if (n == "scan_memo") {
     g.scan_memo = value != 0;
+  } else if (n == "load_memo_log2") {
+    g.load_memo_log2 = (int)value;
   } else if (n == "memo_shift") {
     if (value > 16) return fail(FAUCET_E_ARG, "memo_shift out of range");
     g.memo_shift = (int)value;
@@ -449,6 +452,7 @@ int faucet_session_reset_filters(faucet_session* s) {
   CU(cudaMemsetAsync(s->d_stamps, 0xff, s->tai() * 4, s->stream));
   CU(cudaMemsetAsync(s->d_lctr, 0, sizeof(LoadCounters), s->stream));
   s->stamp_base = 1;
+  s->memo_dirty = true;  // pass 1's cache of saturated k-mers describes the filters that were just emptied
   return 0;
 }
 
@@ -517,6 +521,12 @@ int faucet_session_load(faucet_session* s) {
   a.fused = s->d_fused; a.stamps = s->d_stamps; a.tai_mask = s->tai() - 1; a.base = s->stamp_base;
   a.k = s->k; a.n_hash = s->n_hash; a.ctr = s->d_lctr; a.text = s->d_text; a.complex_list = s->d_complex;
   a.n_complex = s->h_pctr.n_complex;
+  a.memo = nullptr; a.memo_mask = 0; a.memo_qbits = 0;
+  if (g.scan_memo && s->log2_tai >= g.load_memo_log2) {  // filters that do not fit L2: cache the saturated k-mers (load.cuh)
+    int qb = 0;
+    if ((rc = memo_acquire(s, 1, &qb))) return rc;
+    if (s->d_memo) { a.memo = s->d_memo; a.memo_mask = s->memo_entries - 1; a.memo_qbits = qb; }
+  }
 
   // Sub-batches: kernel A treats "all bits already in bloo1 when the sub-batch starts" as contained and
   // only the rest touches the 4-byte-per-bit stamp array, so short early sub-batches (bloo1 fills
@@ -601,8 +611,8 @@ int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_
   return 0;
 }
 
-// The k-mer cache of scan.cuh (kind 2; a pass-1 cache of saturated k-mers, kind 1, was tried and is slower than the
-// three probes of the L2-resident fused filter it replaces).  Cleared when what it caches went stale.  Sized from the filter (~ estimated k-mers); a cache, so a
+// The k-mer cache: one buffer, used by pass 2 (kind 2: extension masks, scan.cuh) and, for filters that do not fit L2, by
+// pass 1 (kind 1: saturated k-mers, load.cuh).  Cleared when its user changes or when what it caches went stale.  Sized from the filter (~ estimated k-mers); a cache, so a
 // short table only costs recomputation.
 static int memo_acquire(faucet_session* s, int kind, int* qbits) {
   if (!s->d_memo) {

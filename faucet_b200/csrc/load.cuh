@@ -49,6 +49,9 @@ struct LoadArgs {
   int k;
   int n_hash;
   LoadCounters* ctr;
+  unsigned long long* memo;       // saturated k-mers (NULL: not used): see load_body_A
+  uint64_t memo_mask;
+  int memo_qbits;
   const uint8_t* text;            // complex-line kernels only
   const uint2* complex_list;
   uint32_t n_complex;
@@ -70,11 +73,35 @@ __device__ __forceinline__ uint64_t inval_window(uint32_t lo, uint32_t hi, int l
   return (((uint64_t)hi << 32) | lo) >> lane;
 }
 
+// A k-mer is SATURATED once every bit of it is set in bloo1 and in bloo2: whatever occurrence of it comes later (in
+// any order: bits are only ever set) is contained in bloo1 and adds nothing to bloo2, i.e. it is a no-op of
+// load_two_filters.  When the filters are too big for L2 (the session enables this from 2^29 bits on), saturated
+// k-mers are remembered in a cache (the table layout of scan.cuh's memo: bijective mix, home slot + quotient, 8
+// probes, one u64 per k-mer) and their later occurrences cost one 8-byte probe instead of two oldHash and n_hash
+// probes of the filter in HBM.  (With an L2-resident filter the probes it saves are cheaper than the one it adds.)
+constexpr int LMEMO_PROBES = 8;
+__device__ __forceinline__ void lmemo_slot(const LoadArgs& a, uint64_t c, uint64_t* home, uint64_t* quot) {
+  uint64_t h = c * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  *home = h >> a.memo_qbits;
+  *quot = h & ((1ull << a.memo_qbits) - 1ull);
+}
+
 template <int NH>
 __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uint32_t t) {
   const int nh = NH ? NH : a.n_hash;
   uint64_t rc = revcomp(fwd, a.k);
   uint64_t c = canon(fwd, rc);
+  uint64_t mhome = 0, mquot = 0;
+  if (a.memo) {
+    lmemo_slot(a, c, &mhome, &mquot);
+#pragma unroll 1
+    for (uint64_t i = 0; i < LMEMO_PROBES; i++) {
+      const unsigned long long e = __ldcg(a.memo + ((mhome + i) & a.memo_mask));
+      if (e == ~0ull) break;
+      if ((e >> 16) == ((i << 44) | mquot)) return false;  // saturated: nothing to do, not pending
+    }
+  }
   uint64_t h0 = hash0(c) & a.tai_mask, h1 = hash1(c) & a.tai_mask;
   uint64_t pos[NH ? NH : MAX_NHASH];
   unsigned long long wd[NH ? NH : MAX_NHASH];
@@ -90,10 +117,21 @@ __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uin
     if (i < nh) all1 &= (bool)((wd[i] >> (pos[i] & 31)) & 1ull);
   if (all1) {
     // contained in bloo1 as of the batch start => Bloom::add on bloo2 (utils/Bloom.h:217-226)
+    bool all2 = true;
 #pragma unroll
     for (int i = 0; i < (NH ? NH : MAX_NHASH); i++)
-      if (i < nh && !((wd[i] >> (32 + (pos[i] & 31))) & 1ull))
+      if (i < nh && !((wd[i] >> (32 + (pos[i] & 31))) & 1ull)) {
+        all2 = false;
         atomicOr(reinterpret_cast<unsigned int*>(a.fused + (uint32_t)(pos[i] >> 5)) + 1, 1u << (pos[i] & 31));
+      }
+    if (all2 && a.memo) {  // both filters already held every bit: remember the k-mer (a cache: give up when crowded)
+#pragma unroll 1
+      for (uint64_t i = 0; i < LMEMO_PROBES; i++) {
+        const unsigned long long word = ((i << 44) | mquot) << 16;
+        const unsigned long long old = atomicCAS(a.memo + ((mhome + i) & a.memo_mask), ~0ull, word);
+        if (old == ~0ull || (old >> 16) == (word >> 16)) break;
+      }
+    }
     return false;
   }
 #pragma unroll

@@ -366,3 +366,24 @@ def test_scan_flags_memo_is_invisible(fb, oracle, small_fq, j):
     finally:
         fb.set_tuning("scan_memo", 1)
         fb.set_batch_bytes(256 << 20)
+
+
+def test_load_saturated_kmer_cache_is_invisible(fb, oracle, small_fq):
+    """pass 1 with its cache of saturated k-mers forced on (it is meant for filters that do not fit L2): same bloo1 and
+    bloo2, same counters, in one batch and in many; and pass 2 right after it re-uses the buffer for its own cache"""
+    _, text = small_fq
+    lt, nh = _geom(oracle, 100000, 50000)
+    o1, o2, ost = oracle.load_two_filters(text, True, 31, lt, nh)
+    orecs, osst = oracle.scan(text, True, True, 1, 31, 1, 100, o2, lt, nh)
+    try:
+        fb.set_tuning("load_memo_log2", 0)
+        for batch in (256 << 20, 300_000):
+            fb.set_batch_bytes(batch)
+            g2, g1, gst = fb.load_two_filters_mem(text, True, 31, lt, nh, want_bloo1=True)
+            assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+            assert gst.kmers == ost.kmers and gst.weight1 == ost.weight1 and gst.weight2 == ost.weight2
+            grecs, gsst = fb.scan_mem(text, True, True, 1, 31, 1, 100, g2, lt, nh)
+            assert gsst == osst and _strip(grecs) == _strip(orecs)
+    finally:
+        fb.set_tuning("load_memo_log2", 29)
+        fb.set_batch_bytes(256 << 20)
