@@ -541,7 +541,17 @@ int faucet_session_load(faucet_session* s) {
     {
       KTimer kt(s, KT_LOAD_A);
       const int grid_a = (int)std::min<uint32_t>(g.sm_count * LOAD_CTAS_PER_SM, (a.w_end - a.w_begin + 7) / 8);  // one full wave
-      DISPATCH_NH(load_A_kernel, s->n_hash, grid_a, LOAD_THREADS, s->stream, a);
+      if (a.memo) {
+        switch (s->n_hash) {
+          case 1: load_A_kernel<1, true><<<grid_a, LOAD_THREADS, 0, s->stream>>>(a); break;
+          case 2: load_A_kernel<2, true><<<grid_a, LOAD_THREADS, 0, s->stream>>>(a); break;
+          case 3: load_A_kernel<3, true><<<grid_a, LOAD_THREADS, 0, s->stream>>>(a); break;
+          case 4: load_A_kernel<4, true><<<grid_a, LOAD_THREADS, 0, s->stream>>>(a); break;
+          default: load_A_kernel<0, true><<<grid_a, LOAD_THREADS, 0, s->stream>>>(a); break;
+        }
+      } else {
+        DISPATCH_NH(load_A_kernel, s->n_hash, grid_a, LOAD_THREADS, s->stream, a);
+      }
       s->launches++;
     }
     if (a.n_complex) {

@@ -87,13 +87,13 @@ __device__ __forceinline__ void lmemo_slot(const LoadArgs& a, uint64_t c, uint64
   *quot = h & ((1ull << a.memo_qbits) - 1ull);
 }
 
-template <int NH>
+template <int NH, bool LM = false>  // LM: with the cache of saturated k-mers (a separate instantiation: the plain one keeps its registers)
 __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uint32_t t) {
   const int nh = NH ? NH : a.n_hash;
   uint64_t rc = revcomp(fwd, a.k);
   uint64_t c = canon(fwd, rc);
   uint64_t mhome = 0, mquot = 0;
-  if (a.memo) {
+  if (LM) {
     lmemo_slot(a, c, &mhome, &mquot);
 #pragma unroll 1
     for (uint64_t i = 0; i < LMEMO_PROBES; i++) {
@@ -124,7 +124,7 @@ __device__ __forceinline__ bool load_body_A(const LoadArgs& a, uint64_t fwd, uin
         all2 = false;
         atomicOr(reinterpret_cast<unsigned int*>(a.fused + (uint32_t)(pos[i] >> 5)) + 1, 1u << (pos[i] & 31));
       }
-    if (all2 && a.memo) {  // both filters already held every bit: remember the k-mer (a cache: give up when crowded)
+    if (LM && all2) {  // both filters already held every bit: remember the k-mer (a cache: give up when crowded)
 #pragma unroll 1
       for (uint64_t i = 0; i < LMEMO_PROBES; i++) {
         const unsigned long long word = ((i << 44) | mquot) << 16;
@@ -167,7 +167,7 @@ __device__ __forceinline__ bool load_body_B(const LoadArgs& a, uint64_t fwd, uin
   return contained;
 }
 
-template <int NH>
+template <int NH, bool LM = false>
 __global__ void __launch_bounds__(LOAD_THREADS, 6) load_A_kernel(LoadArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * LOAD_THREADS + threadIdx.x) >> 5;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(LOAD_THREADS, 6) load_A_kernel(LoadArgs a) {
     bool pending = false;
     if (valid) {
       uint32_t p = (w << 5) + lane;
-      pending = load_body_A<NH>(a, kmer_at(a.packed, p, a.k), a.base + p);
+      pending = load_body_A<NH, LM>(a, kmer_at(a.packed, p, a.k), a.base + p);
     }
     uint32_t pb = __ballot_sync(0xffffffffu, pending);
     if (lane == 0) {
