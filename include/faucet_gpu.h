@@ -119,10 +119,19 @@ void faucet_gpu_free(void* p);
 int faucet_gpu_set_batch_bytes(size_t bytes);
 int faucet_gpu_set_epoch_limit(uint64_t stamps);
 int faucet_gpu_get_timings(faucet_timings* out);
-/* knobs of the GPU junction stitch (tests shrink them to force table growth, deferrals and buffer
- * drains): "table_cap0" initial junction-table slots (power of two), "res_log2" log2 of the
- * reservation-table entries, "stitch_w0" / "stitch_w_max" initial / maximal records per round,
- * "ext_cap0" u64 words of the extension-list buffer that feeds the long pair filter */
+/* Knobs (none changes a result; tests use them to force every code path).  Setting one drops the cached session.
+ *  stitch:  "stitch_impl" 1 = one warp per record (default), 2 = lanes share the lookups and one thread walks a record,
+ *           with reader/writer reservations; "table_cap0" initial junction-table slots (power of two, grows by rehash at
+ *           load 1/2); "res_log2" log2 of the reservation-table entries; "stitch_w0" / "stitch_w_max" initial / maximal
+ *           records per round; "stitch_shrink_den" / "stitch_grow_den" window adaptation; "stitch_blocks" resident CTAs
+ *           per SM (2..4); "rows_max" records whose reservation rows are listed per launch (impl 2); "ext_cap0" u64
+ *           words of the extension-list buffer that feeds the long pair filter
+ *  scan:    "scan_memo" 1 = scan_flags caches the extension masks of every k-mer it has computed (default), 0 = every
+ *           position from the Bloom filter; "memo_shift" cache entries = Bloom bits >> memo_shift (8 bytes each)
+ *  load:    "load_sub_bytes0" / "load_sub_bytes" first / largest sub-batch of pass 1; "load_memo_log2" pass 1 caches
+ *           saturated k-mers when the filter has at least 2^this bits (default 29: filters that do not fit L2)
+ *  passes:  "retain_planes" 1 = pass 1 keeps the parsed planes in HBM for faucet_gpu_scan_retained, within
+ *           "retain_budget" bytes (default 64 GiB) */
 int faucet_gpu_set_tuning(const char* name, uint64_t value);
 
 /* ---- device-resident stage API (bench.py "value": inputs already in HBM) ------------------
