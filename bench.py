@@ -277,14 +277,14 @@ def run_ours(args, w):
     barrier()
     clk = clocks.stop()
     launches = sess.launches - launches0
-    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch")}
+    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry")}
     sess.set_profiling(False)
     lstats = sess.load_stats()
     stitch_info, n_junc = {}, 0
     if rank == 0:
         recs, _ = sess.junctions()  # gathers the map once (not timed); publishes the stitch round counters
         n_junc = len(recs)
-        stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith("stitch_")}
+        stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith(("stitch_", "epoch", "exact_", "dry_", "nonquiet", "writer"))}
     b2, _ = sess.get_bloom_full() if world > 1 else sess.get_bloom()
     weight2 = float(np.unpackbits(b2).sum()) / (1 << lt)
 

@@ -42,7 +42,9 @@ class LoadStats(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "parse_ms", "load_ms", "scan_ms", "stitch_ms", "d2h_ms", "total_ms")] + \
                [(n, C.c_uint64) for n in ("kernel_launches", "stitch_rounds", "stitch_deferred")] + \
-               [("stitch_phase_ns", C.c_uint64 * 8)]
+               [("stitch_phase_ns", C.c_uint64 * 8)] + \
+               [(n, C.c_uint64) for n in ("epochs_exact", "epochs_classify", "exact_records", "dry_records", "epoch_iterations",
+                                          "epoch_fallbacks", "nonquiet_records", "writer_records")]
 
 
 _u8p = C.POINTER(C.c_uint8)
@@ -246,7 +248,7 @@ def scan(path, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, lo
 
 class Session:
     """device-resident stage API (faucet_session_* in include/faucet_gpu.h)"""
-    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4}
+    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4, "stitch_dry": 5}
 
     def __init__(self, k, log2_tai, n_hash, j=1, max_spacer_dist=100, max_text_bytes=1 << 30):
         self.h = C.c_void_p()

@@ -20,7 +20,6 @@
 #include "scan.cuh"
 #include "pair_filter_host.hpp"
 #include "stitch.cuh"
-#include "stitch2.cuh"
 
 using namespace faucet;
 
@@ -37,8 +36,12 @@ struct Global {
   int res_log2 = 24;                           // reservation table entries (u32 each)
   uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048, stitch_shrink_den = 4, stitch_grow_den = 10;
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
-  int stitch_impl = 1;    // 1: one warp per record (stitch.cuh, the faster one as measured); 2: one thread walks a record (stitch2.cuh)
-  size_t rows_max = (size_t)1 << 22;  // stitch2: records whose reservation rows are listed per launch
+  // epochs of the stitch (stitch.cuh): 0 = one ordered run per batch, 1 = adaptive (ordered while most records write,
+  // then classify / execute / verify / apply), 2 = classify from the first record on (tests)
+  int epoch_mode = 1;
+  uint32_t epoch0 = 8192, epoch_max = 1u << 20;  // first / largest epoch, records
+  uint32_t epoch_switch_pct = 30;                // an ordered epoch with fewer writers than this switches to classify epochs
+  uint32_t epoch_shrink_pct = 14, epoch_grow_pct = 6;  // exact-set share above / below which the epoch halves / doubles
   int load_memo_log2 = 29;            // pass 1 caches saturated k-mers when the filter has at least 2^this bits
   int memo_shift = 1;                 // memo entries = Bloom bits >> memo_shift (8 bytes each): load <= ~0.3 of the 8-probe cache
   bool scan_memo = true;              // scan_flags looks the extension masks of a k-mer up before it computes them (scan.cuh)
@@ -63,7 +66,7 @@ int fail(int code, const std::string& msg) {
 
 constexpr size_t TAIL_MAX = (size_t)1 << 24;  // longest partial record carried between batches
 constexpr size_t TEXT_PAD = 2 * PARSE_CHUNK;
-enum { KT_PARSE = 0, KT_LOAD_A, KT_LOAD_B, KT_SCAN, KT_STITCH, KT_COUNT };
+enum { KT_PARSE = 0, KT_LOAD_A, KT_LOAD_B, KT_SCAN, KT_STITCH, KT_DRY, KT_COUNT };
 
 }  // namespace
 
@@ -109,7 +112,20 @@ struct faucet_session {
   uint32_t* d_recs = nullptr;   // REC_WORDS u32 per slot
   unsigned long long tbl_cap = 0;
   uint32_t* d_res = nullptr;
-  uint32_t* d_resw = nullptr;   // stitch2: writers' reservations
+  uint32_t* d_dirty = nullptr;  // epochs: smallest record that wrote a junction under each reservation slot
+  uint8_t* d_in_exact = nullptr;  // epochs: per record of the batch, member of the exact set
+  size_t in_exact_cap = 0;
+  uint32_t *d_list = nullptr, *d_eprefix = nullptr, *d_eprefix_sums = nullptr, *d_count = nullptr;  // the exact set as an ascending list
+  size_t list_cap = 0;
+  unsigned long long* d_snap_keys = nullptr;  // epochs: the table as it stood when the epoch began (T0)
+  uint32_t* d_snap_recs = nullptr;
+  unsigned long long snap_cap = 0;
+  StitchState* d_st_snap = nullptr;
+  StitchState h_st{};           // host copy of the stitch state after the last ordered run / apply
+  uint32_t* d_spf_snap = nullptr;
+  uint32_t ep_size = 0;         // records of the next epoch
+  bool ep_exact = true;         // the next epoch runs entirely through the ordered kernel
+  struct EpochStats { uint64_t exact_epochs = 0, classify_epochs = 0, exact_runs = 0, dry_records = 0, iterations = 0, fallbacks = 0, nonquiet = 0; } ep;
   uint32_t* d_deferred[2] = {nullptr, nullptr};
   uint32_t w_max = 0, deferred_cap = 0;
   uint32_t* d_spf = nullptr;    // device copy of the short pair filter
@@ -134,9 +150,6 @@ struct faucet_session {
   uint64_t retained_lines = 0;
   char* h_stage[3] = {nullptr, nullptr, nullptr};  // pinned staging buffers of the file reader (whole-pass entry points)
   size_t h_stage_cap = 0;
-  int impl = 0;                 // stitch kernel this session's flag buffer is laid out for (g.stitch_impl at creation)
-  uint32_t* d_rows = nullptr;   // stitch2: reservation rows of the records [row_base, row_end)
-  size_t rows_cap = 0;
   uint32_t *d_hist = nullptr, *d_hist_sums = nullptr;  // junction-creation counts per record (ordering)
   unsigned long long hist_cap = 0;
   faucet_junction_rec* d_out = nullptr;
@@ -288,9 +301,16 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "stitch_blocks") {
     if (value < 2 || value > 4) return fail(FAUCET_E_ARG, "stitch_blocks must be 2, 3 or 4");
     g.stitch_blocks = (int)value;
-  } else if (n == "stitch_impl") {
-    if (value != 1 && value != 2) return fail(FAUCET_E_ARG, "stitch_impl must be 1 (warp per record) or 2 (thread per record)");
-    g.stitch_impl = (int)value;
+  } else if (n == "epoch_mode") {
+    if (value > 2) return fail(FAUCET_E_ARG, "epoch_mode must be 0 (one ordered run), 1 (adaptive) or 2 (always classify)");
+    g.epoch_mode = (int)value;
+  } else if (n == "epoch0" || n == "epoch_max") {
+    if (value < 1 || value > (1u << 30)) return fail(FAUCET_E_ARG, "epoch size out of range");
+    (n == "epoch0" ? g.epoch0 : g.epoch_max) = (uint32_t)value;
+    if (g.epoch_max < g.epoch0) g.epoch_max = g.epoch0;
+  } else if (n == "epoch_switch_pct" || n == "epoch_shrink_pct" || n == "epoch_grow_pct") {
+    if (value > 100) return fail(FAUCET_E_ARG, "percentage out of range");
+    (n == "epoch_switch_pct" ? g.epoch_switch_pct : n == "epoch_shrink_pct" ? g.epoch_shrink_pct : g.epoch_grow_pct) = (uint32_t)value;
   } else if (n == "scan_memo") {
     g.scan_memo = value != 0;
   } else if (n == "load_memo_log2") {
@@ -302,9 +322,6 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
     g.retain_planes = value != 0;
   } else if (n == "retain_budget") {
     g.retain_budget = (size_t)value;
-  } else if (n == "rows_max") {
-    if (value < 1 || value > ((uint64_t)1 << 26)) return fail(FAUCET_E_ARG, "rows_max out of range");
-    g.rows_max = (size_t)value;
   } else if (n == "stitch_w0") {
     if (value < 1) return fail(FAUCET_E_ARG, "stitch_w0 out of range");
     g.stitch_w0 = (uint32_t)value;
@@ -337,7 +354,6 @@ int faucet_session_create(faucet_session** out, int k, int log2_tai, int n_hash,
   if (max_text_bytes > ((size_t)3 << 30)) return fail(FAUCET_E_ARG, "a batch must stay below 3 GiB");
   faucet_session* s = new faucet_session();
   s->k = k; s->log2_tai = log2_tai; s->n_hash = n_hash; s->j = j; s->max_spacer = max_spacer_dist;
-  s->impl = g.stitch_impl;
   s->cap = ((max_text_bytes + TAIL_MAX + PARSE_CHUNK - 1) / PARSE_CHUNK) * PARSE_CHUNK;
   int rc = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -381,8 +397,10 @@ void faucet_session_destroy(faucet_session* s) {
   retained_free(s);
   for (int i = 0; i < 3; i++) if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
   if (s->h_recs) cudaFreeHost(s->h_recs);
-  cudaFree(s->d_rows); cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
-  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res); cudaFree(s->d_resw);
+  cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
+  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res); cudaFree(s->d_dirty); cudaFree(s->d_in_exact);
+  cudaFree(s->d_list); cudaFree(s->d_eprefix); cudaFree(s->d_eprefix_sums); cudaFree(s->d_count); cudaFree(s->d_snap_keys); cudaFree(s->d_snap_recs);
+  cudaFree(s->d_st_snap); cudaFree(s->d_spf_snap);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   faucet_session_close_peers(s);
   cudaFree(s->d_b1local); cudaFree(s->d_hist); cudaFree(s->d_hist_sums); cudaFree(s->d_out);
@@ -654,7 +672,6 @@ int faucet_session_scan_flags(faucet_session* s) {
   ScanArgs a;
   a.inval = s->d_inval; a.packed = s->d_packed; a.n_words = (uint32_t)((s->n + 31) / 32);
   a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
-  a.fplanes = s->impl == 2 ? reinterpret_cast<uint32_t*>(s->d_flags) : nullptr;
   const int grid = g.sm_count * SCAN_CTAS_PER_SM * 2;  // two full waves of resident CTAs
   a.memo = nullptr; a.memo_mask = 0; a.dbg = nullptr;
   static unsigned long long* d_dbg = nullptr;
@@ -685,29 +702,43 @@ int faucet_session_scan_flags(faucet_session* s) {
 
 // ---- pass 2, stream-order part: GPU junction table (stitch.cuh) ------------------------------------
 
-static int stitch_alloc_table(faucet_session* s, unsigned long long cap) {
+static int stitch_alloc_into(faucet_session* s, unsigned long long cap, unsigned long long** keys, uint32_t** recs,
+                             unsigned long long** stamps) {
+  *keys = nullptr; *recs = nullptr; *stamps = nullptr;
   int rc;
-  if ((rc = dmalloc(&s->d_keys, cap + 1)) || (rc = dmalloc(&s->d_recs, (cap + 1) * REC_WORDS)) || (rc = dmalloc(&s->d_jstamps, cap + 1)))
+  if ((rc = dmalloc(keys, cap + 1)) || (rc = dmalloc(recs, (cap + 1) * REC_WORDS)) || (rc = dmalloc(stamps, cap + 1))) {
+    cudaFree(*keys); cudaFree(*recs); cudaFree(*stamps);
+    *keys = nullptr; *recs = nullptr; *stamps = nullptr;
     return rc;
-  CU(cudaMemsetAsync(s->d_keys, 0xff, (cap + 1) * 8, s->stream));
-  CU(cudaMemsetAsync(s->d_recs, 0, (cap + 1) * REC_WORDS * 4, s->stream));
-  CU(cudaMemsetAsync(s->d_jstamps, 0, (cap + 1) * 8, s->stream));
+  }
+  CU(cudaMemsetAsync(*keys, 0xff, (cap + 1) * 8, s->stream));
+  CU(cudaMemsetAsync(*recs, 0, (cap + 1) * REC_WORDS * 4, s->stream));
+  CU(cudaMemsetAsync(*stamps, 0, (cap + 1) * 8, s->stream));
+  return 0;
+}
+
+static int stitch_alloc_table(faucet_session* s, unsigned long long cap) {
+  int rc = stitch_alloc_into(s, cap, &s->d_keys, &s->d_recs, &s->d_jstamps);
+  if (rc) return rc;
   s->tbl_cap = cap;
   return 0;
 }
 
+// doubles the table by rehash; on failure the old table stays in place
 static int stitch_grow_table(faucet_session* s) {
-  unsigned long long *ok = s->d_keys, *os = s->d_jstamps;
-  uint32_t* orc = s->d_recs;
   const unsigned long long ocap = s->tbl_cap;
-  s->d_keys = nullptr; s->d_recs = nullptr; s->d_jstamps = nullptr;
-  int rc = stitch_alloc_table(s, ocap * 2);
+  if (ocap * 2 >= (1ull << 31)) return fail(FAUCET_E_NOMEM, "junction table would exceed 2^31 slots");
+  unsigned long long *nk, *ns;
+  uint32_t* nr;
+  int rc = stitch_alloc_into(s, ocap * 2, &nk, &nr, &ns);
   if (rc) return rc;
-  stitch_rehash_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(ok, orc, os, ocap, s->d_keys, s->d_recs, s->d_jstamps, s->tbl_cap);
+  stitch_rehash_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(s->d_keys, s->d_recs, s->d_jstamps, ocap, nk, nr, ns, ocap * 2);
   s->launches++;
   CU(cudaStreamSynchronize(s->stream));
-  cudaFree(ok); cudaFree(orc); cudaFree(os);
-  return check_launch("stitch_rehash");
+  if ((rc = check_launch("stitch_rehash"))) { cudaFree(nk); cudaFree(nr); cudaFree(ns); return rc; }
+  cudaFree(s->d_keys); cudaFree(s->d_recs); cudaFree(s->d_jstamps);
+  s->d_keys = nk; s->d_recs = nr; s->d_jstamps = ns; s->tbl_cap = ocap * 2;
+  return 0;
 }
 
 int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_cleaning, uint8_t* short_pf,
@@ -715,7 +746,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
                                 int lpf_n_hash) {
   int rc;
   s->paired = paired_ends; s->no_cleaning = no_cleaning;
-  if (!s->d_st && (rc = dmalloc(&s->d_st, 1))) return rc;
+  if (!s->d_st && ((rc = dmalloc(&s->d_st, 1)) || (rc = dmalloc(&s->d_st_snap, 1)) || (rc = dmalloc(&s->d_count, 1)))) return rc;
   if (!s->d_keys) {
     if ((rc = stitch_alloc_table(s, g.table_cap0))) return rc;
   } else {  // a new scan starts from an empty JunctionMap
@@ -723,15 +754,6 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     CU(cudaMemsetAsync(s->d_recs, 0, (s->tbl_cap + 1) * REC_WORDS * 4, s->stream));
   }
   s->w_max = g.stitch_w_max;
-  if (!s->stitch_grid && s->impl == 2) {
-    int per_sm = 0;
-    const size_t smem = S2_SMEM;
-    s->stitch_fn = (const void*)stitch2_kernel;
-    CU(cudaFuncSetAttribute(s->stitch_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->stitch_fn, S2_THREADS, smem));
-    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch2_kernel cannot be made resident");
-    s->stitch_grid = g.sm_count;  // one CTA per SM: the cheapest grid barrier
-  }
   if (!s->stitch_grid) {
     int per_sm = 0;
     const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
@@ -745,15 +767,11 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_kernel cannot be made resident");
     s->stitch_grid = per_sm * g.sm_count;
   }
-  // one record per warp (thread) per round
-  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * (s->impl == 2 ? S2_WARPS * S2_RPW : STITCH_WARPS));
+  // one record per warp per round
+  s->w_max = std::min<uint32_t>(s->w_max, (uint32_t)s->stitch_grid * STITCH_WARPS);
   if (!s->d_res) {
     if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
-  }
-  if (s->impl == 2 && !s->d_resw) {
-    if ((rc = dmalloc(&s->d_resw, (size_t)1 << g.res_log2))) return rc;
-    CU(cudaMemsetAsync(s->d_resw, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
   }
   if (s->w_max > s->deferred_cap) {
     for (int i = 0; i < 2; i++) {
@@ -765,13 +783,14 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   CU(cudaMemsetAsync(s->d_st, 0, sizeof(StitchState), s->stream));
   unsigned int w0 = std::min(g.stitch_w0, s->w_max);
   CU(cudaMemcpyAsync(&s->d_st->W, &w0, 4, cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemsetAsync(s->d_st->min_w, 0xff, sizeof(s->d_st->min_w), s->stream));
+  s->h_st = StitchState();
   // short pair filter: adds only (src/ReadScanner.cpp:208-225) => atomicOr on a device copy
   cudaFree(s->d_spf); s->d_spf = nullptr; s->h_spf = nullptr;
+  cudaFree(s->d_spf_snap); s->d_spf_snap = nullptr;
   if (short_pf && !no_cleaning) {
     size_t words = ((size_t)1 << spf_log2_tai) / 32;
     if (words == 0) words = 1;
-    if ((rc = dmalloc(&s->d_spf, words))) return rc;
+    if ((rc = dmalloc(&s->d_spf, words)) || (rc = dmalloc(&s->d_spf_snap, words))) return rc;
     CU(cudaMemcpyAsync(s->d_spf, short_pf, ((size_t)1 << spf_log2_tai) / 8, cudaMemcpyHostToDevice, s->stream));
     s->h_spf = short_pf; s->spf_log2 = spf_log2_tai; s->spf_nh = spf_n_hash;
   }
@@ -788,108 +807,245 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   s->rec_base = 0;
   s->n_recs_out = 0;
   std::memset(&s->sstats, 0, sizeof s->sstats);
+  s->ep_size = g.epoch0;
+  s->ep_exact = true;
+  s->ep = faucet_session::EpochStats();
   s->stitching = true;
   return 0;
 }
 
-// runs the stitch over the parsed + flagged batch that is resident in the session
-int faucet_session_stitch_batch(faucet_session* s) {
-  if (!s->stitching) return fail(FAUCET_E_STATE, "stitch_begin not called");
-  if (!s->parsed) return fail(FAUCET_E_STATE, "stitch_batch before parse");
-  const bool want_ext = s->lpf.enabled();
-  struct { unsigned int next, nd[2]; } z = {0, {0, 0}};
-  CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
-  s->h_ext.clear();
-  uint32_t row_base = 0, row_end = s->n_recs;
-  bool rows_ready = false;
-  if (s->impl == 2) {
-    row_end = (uint32_t)std::min<size_t>(s->n_recs, g.rows_max);
-    const size_t need = std::max<size_t>(1, row_end);
-    if (need > s->rows_cap) {
-      cudaFree(s->d_rows); s->d_rows = nullptr;
-      int rc = dmalloc(&s->d_rows, need * S2_ROW);
-      if (rc) return rc;
-      s->rows_cap = need;
-    }
+static void stitch_fill_args(faucet_session* s, StitchArgs& a) {
+  std::memset(&a, 0, sizeof a);
+  a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->d_flags;
+  a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
+  a.k = s->k; a.j = s->j; a.spacer = s->max_spacer; a.no_cleaning = s->no_cleaning; a.paired = s->paired;
+  a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
+  a.res = s->d_res; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
+  a.deferred[0] = s->d_deferred[0]; a.deferred[1] = s->d_deferred[1];
+  a.st = s->d_st; a.special = &s->d_st->special;
+  a.spf = s->d_spf; a.spf_mask = s->d_spf ? ((1ull << s->spf_log2) - 1) : 0; a.spf_nh = s->spf_nh;
+  a.ext = s->lpf.enabled() ? s->d_ext : nullptr; a.ext_cap = s->ext_cap;
+  a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
+  a.shrink_den = g.stitch_shrink_den; a.grow_den = g.stitch_grow_den;
+}
+
+// moves what the kernels left in the extension-list buffer to the host
+static int stitch_drain_ext(faucet_session* s) {
+  unsigned long long used = 0;
+  CU(cudaMemcpyAsync(&used, &s->d_st->ext_used, 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (used) {
+    const size_t at = s->h_ext.size();
+    s->h_ext.resize(at + used);
+    CU(cudaMemcpy(s->h_ext.data() + at, s->d_ext, used * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemsetAsync(&s->d_st->ext_used, 0, 8, s->stream));
   }
+  return 0;
+}
+
+// The ordered kernel over the entries [begin, end) of `list` (NULL: the records themselves), relaunched until done.
+// allow_grow: grow the table when a round could overfill it; otherwise *need_grow is set and the caller decides
+// (inside a classify epoch the slots of the snapshot must stay valid).
+static int stitch_run_ordered(faucet_session* s, const uint32_t* list, uint32_t begin, uint32_t end, bool mark_dirty,
+                              bool allow_grow, bool* need_grow) {
+  if (need_grow) *need_grow = false;
+  struct { unsigned int next, nd[2]; } z = {begin, {0, 0}};
+  CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
   while (true) {
     StitchArgs a;
-    a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->impl == 2 ? nullptr : s->d_flags;
-    a.fplanes = s->impl == 2 ? reinterpret_cast<const uint32_t*>(s->d_flags) : nullptr;
-    a.rows = s->d_rows; a.row_base = row_base; a.row_end = row_end;
-    a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
-    a.k = s->k; a.j = s->j; a.spacer = s->max_spacer; a.no_cleaning = s->no_cleaning; a.paired = s->paired;
-    a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
-    a.res = s->d_res; a.resw = s->d_resw; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
-    a.deferred[0] = s->d_deferred[0]; a.deferred[1] = s->d_deferred[1];
-    a.st = s->d_st;
-    a.spf = s->d_spf; a.spf_mask = s->d_spf ? ((1ull << s->spf_log2) - 1) : 0; a.spf_nh = s->spf_nh;
-    a.ext = want_ext ? s->d_ext : nullptr; a.ext_cap = s->ext_cap;
-    a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
-    a.shrink_den = g.stitch_shrink_den; a.grow_den = g.stitch_grow_den;
+    stitch_fill_args(s, a);
+    a.n_recs = end; a.list = list;
+    a.dirty = mark_dirty ? s->d_dirty : nullptr;
     void* params[] = {&a};
     {
       KTimer kt(s, KT_STITCH);
-      if (s->impl == 2) {
-        if (!rows_ready && row_end > row_base) {  // pure function of the text: the minimizer slots of every record
-          stitch2_rows_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(a, s->d_rows);
-          s->launches++;
-          rows_ready = true;
-        }
-        CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(S2_THREADS), params, S2_SMEM, s->stream));
-      } else {
-        CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(STITCH_THREADS), params,
-                                       STITCH_WARPS * sizeof(WarpScratch), s->stream));
-      }
+      CU(cudaLaunchCooperativeKernel(s->stitch_fn, dim3(s->stitch_grid), dim3(STITCH_THREADS), params,
+                                     STITCH_WARPS * sizeof(WarpScratch), s->stream));
       s->launches++;
     }
-    unsigned int status = 0;
-    CU(cudaMemcpyAsync(&status, &s->d_st->status, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     int rc = check_launch("stitch");
     if (rc) return rc;
+    const unsigned int status = s->h_st.status;
     if (status == ST_DONE) break;
-    if (status == ST_STUCK) {
-      StitchState st;
-      cudaMemcpy(&st, s->d_st, sizeof st, cudaMemcpyDeviceToHost);
-      char msg[256];
-      snprintf(msg, sizeof msg, "stitch: a round executed no record (internal error): window %llu, writers %llu, blocked %llu, first record %llu flags %llu, round %u, W %u, min_w %u %u",
-               st.stats[SS_T_P1C], st.stats[SS_T_P2A], st.stats[SS_T_P1B], st.max_need >> 8, st.max_need & 255, st.round, st.W, st.min_w[0], st.min_w[1]);
-      return fail(FAUCET_E_CUDA, msg);
-    }
     // an aborted round leaves its reservations behind
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
-    if (s->d_resw) CU(cudaMemsetAsync(s->d_resw, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
-    if (status == ST_MORE_ROWS) {  // every record of [row_base, row_end) is done: list the next ones
-      row_base = row_end;
-      row_end = (uint32_t)std::min<size_t>(s->n_recs, (size_t)row_base + g.rows_max);
-      rows_ready = false;
-    } else if (status == ST_GROW_TABLE) {
+    if (status == ST_GROW_TABLE) {
+      if (!allow_grow) { *need_grow = true; return 0; }
       if ((rc = stitch_grow_table(s))) return rc;
     } else if (status == ST_DRAIN_EXT) {
-      unsigned long long used = 0;
-      CU(cudaMemcpy(&used, &s->d_st->ext_used, 8, cudaMemcpyDeviceToHost));
-      if (used == 0) {  // one round alone does not fit: a bigger buffer
+      if (s->h_st.ext_used == 0) {  // one round alone does not fit: a bigger buffer
         cudaFree(s->d_ext); s->d_ext = nullptr;
         s->ext_cap *= 2;
         if ((rc = dmalloc(&s->d_ext, s->ext_cap))) return rc;
-      } else {
-        size_t at = s->h_ext.size();
-        s->h_ext.resize(at + used);
-        CU(cudaMemcpy(s->h_ext.data() + at, s->d_ext, used * 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemsetAsync(&s->d_st->ext_used, 0, 8, s->stream));
+      } else if ((rc = stitch_drain_ext(s))) {
+        return rc;
       }
     } else {
       return fail(FAUCET_E_CUDA, "stitch kernel returned an unknown status");
     }
   }
+  return 0;
+}
+
+static int stitch_ensure_epoch_buffers(faucet_session* s, uint32_t m) {
+  int rc;
+  if (s->n_recs > s->in_exact_cap) {
+    cudaFree(s->d_in_exact); s->d_in_exact = nullptr;
+    s->in_exact_cap = (size_t)s->n_recs + s->n_recs / 4 + 1024;
+    if ((rc = dmalloc(&s->d_in_exact, s->in_exact_cap))) return rc;
+  }
+  if (m > s->list_cap) {
+    cudaFree(s->d_list); cudaFree(s->d_eprefix); cudaFree(s->d_eprefix_sums);
+    s->d_list = nullptr; s->d_eprefix = nullptr; s->d_eprefix_sums = nullptr;
+    s->list_cap = (size_t)m + m / 4 + 1024;
+    if ((rc = dmalloc(&s->d_list, s->list_cap)) || (rc = dmalloc(&s->d_eprefix, s->list_cap)) ||
+        (rc = dmalloc(&s->d_eprefix_sums, s->list_cap / SCAN_CHUNK + 2)))
+      return rc;
+  }
+  if (!s->d_dirty && (rc = dmalloc(&s->d_dirty, (size_t)1 << g.res_log2))) return rc;
+  if (s->snap_cap != s->tbl_cap) {
+    cudaFree(s->d_snap_keys); cudaFree(s->d_snap_recs);
+    s->d_snap_keys = nullptr; s->d_snap_recs = nullptr; s->snap_cap = 0;
+    if ((rc = dmalloc(&s->d_snap_keys, s->tbl_cap + 1)) || (rc = dmalloc(&s->d_snap_recs, (s->tbl_cap + 1) * REC_WORDS))) return rc;
+    s->snap_cap = s->tbl_cap;
+  }
+  return 0;
+}
+
+// T0 := the live table (keys and records; creation stamps of T0 keys never change), the stitch state and the short pair filter
+static int stitch_snapshot(faucet_session* s) {
+  CU(cudaMemcpyAsync(s->d_snap_keys, s->d_keys, (s->tbl_cap + 1) * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_snap_recs, s->d_recs, (s->tbl_cap + 1) * REC_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_st_snap, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToDevice, s->stream));
+  if (s->d_spf) CU(cudaMemcpyAsync(s->d_spf_snap, s->d_spf, std::max<size_t>(4, ((size_t)1 << s->spf_log2) / 8), cudaMemcpyDeviceToDevice, s->stream));
+  return 0;
+}
+static int stitch_restore(faucet_session* s, size_t h_ext_mark) {
+  CU(cudaMemcpyAsync(s->d_keys, s->d_snap_keys, (s->tbl_cap + 1) * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_recs, s->d_snap_recs, (s->tbl_cap + 1) * REC_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_st, s->d_st_snap, sizeof(StitchState), cudaMemcpyDeviceToDevice, s->stream));
+  if (s->d_spf) CU(cudaMemcpyAsync(s->d_spf, s->d_spf_snap, std::max<size_t>(4, ((size_t)1 << s->spf_log2) / 8), cudaMemcpyDeviceToDevice, s->stream));
+  s->h_ext.resize(h_ext_mark);
+  return 0;
+}
+
+// One epoch of the classify / execute / verify / apply scheme (stitch.cuh) over the records [r, r + m).
+static int stitch_epoch_classify(faucet_session* s, uint32_t r, uint32_t m, uint32_t* n_exact_out) {
+  int rc;
+  // headroom the ordered kernel itself would ask for, before the snapshot pins the slots
+  while (s->h_st.n_entries + s->h_st.max_need * s->w_max > s->tbl_cap / 2)
+    if ((rc = stitch_grow_table(s))) return rc;
+  if ((rc = stitch_ensure_epoch_buffers(s, m))) return rc;
+  const int grid = g.sm_count * 8;
+  StitchArgs d;
+  stitch_fill_args(s, d);
+  d.keys = s->d_snap_keys; d.recs = s->d_snap_recs; d.special = &s->d_st_snap->special;
+  d.cov_out = s->d_recs; d.in_exact = s->d_in_exact; d.r_begin = r; d.r_end = r + m; d.dirty = s->d_dirty;
+  if ((rc = stitch_snapshot(s))) return rc;
+  CU(cudaMemsetAsync(s->d_in_exact + r, 0, m, s->stream));
+  {
+    KTimer kt(s, KT_DRY);
+    d.dry_mode = DRY_CLASSIFY;
+    stitch_dry_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
+    s->launches++;
+  }
+  CU(cudaMemcpyAsync(s->d_st_snap, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToDevice, s->stream));  // keeps classify's counters
+  const size_t h_ext_mark = s->h_ext.size();
+  const unsigned n_blocks = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  uint32_t n_exact = 0, n_prev = 0;
+  for (int iter = 0;; iter++) {
+    {
+      KTimer kt(s, KT_DRY);
+      exact_flags_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix);
+      scan_reduce_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
+      scan_sums_kernel<<<1, 1024, 0, s->stream>>>(s->d_eprefix_sums, n_blocks);
+      scan_apply_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
+      exact_list_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix, s->d_list, s->d_count);
+      s->launches += 5;
+    }
+    CU(cudaMemcpyAsync(&n_exact, s->d_count, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if ((rc = check_launch("stitch_list"))) return rc;
+    if (iter == 0) s->ep.nonquiet += n_exact;
+    if (n_exact == 0 || (iter > 0 && n_exact == n_prev)) break;  // nothing (more) joined: the live table is final
+    if (iter > 0 && (rc = stitch_restore(s, h_ext_mark))) return rc;
+    CU(cudaMemsetAsync(s->d_dirty, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+    bool need_grow = false;
+    if ((rc = stitch_run_ordered(s, s->d_list, 0, n_exact, true, false, &need_grow))) return rc;
+    s->ep.exact_runs += n_exact;
+    s->ep.iterations++;
+    if (need_grow) {  // the slots of T0 are about to move: undo the epoch, grow, and take it in order instead
+      if ((rc = stitch_restore(s, h_ext_mark)) || (rc = stitch_grow_table(s))) return rc;
+      s->ep.fallbacks++;
+      *n_exact_out = m;
+      return stitch_run_ordered(s, nullptr, r, r + m, false, true, nullptr);
+    }
+    {
+      KTimer kt(s, KT_DRY);
+      stitch_verify_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
+      s->launches++;
+    }
+    n_prev = n_exact;
+  }
+  // apply: the records outside the exact set, against T0
+  d.st = s->d_st;
+  d.dry_mode = DRY_APPLY;
+  if (!d.ext) {
+    KTimer kt(s, KT_DRY);
+    stitch_dry_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
+    s->launches++;
+  } else {  // bounded launches: a quiet record emits at most LAND_CAP extensions plus chunk headers
+    const uint32_t per_rec = LAND_CAP + LAND_CAP / (EXT_STAGE - 1) + 2;
+    for (uint32_t x = r; x < r + m;) {
+      if ((rc = stitch_drain_ext(s))) return rc;
+      const uint32_t fit = (uint32_t)std::max<unsigned long long>(1, s->ext_cap / per_rec);
+      d.r_begin = x; d.r_end = (uint32_t)std::min<uint64_t>((uint64_t)x + fit, (uint64_t)r + m);
+      KTimer kt(s, KT_DRY);
+      stitch_dry_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
+      s->launches++;
+      x = d.r_end;
+    }
+  }
+  CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if ((rc = check_launch("stitch_apply"))) return rc;
+  if (s->h_st.stats[SS_DRY_ERROR]) return fail(FAUCET_E_CUDA, "stitch: apply met a record that is not quiet (internal error)");
+  *n_exact_out = n_exact;
+  return 0;
+}
+
+// runs the stitch over the parsed + flagged batch that is resident in the session, epoch by epoch
+int faucet_session_stitch_batch(faucet_session* s) {
+  if (!s->stitching) return fail(FAUCET_E_STATE, "stitch_begin not called");
+  if (!s->parsed) return fail(FAUCET_E_STATE, "stitch_batch before parse");
+  const bool want_ext = s->lpf.enabled();
+  s->h_ext.clear();
+  int rc;
+  for (uint32_t r = 0; r < s->n_recs;) {
+    const uint32_t m = g.epoch_mode == 0 ? s->n_recs - r : (uint32_t)std::min<uint64_t>(s->ep_size, s->n_recs - r);
+    const bool classify = g.epoch_mode == 2 || (g.epoch_mode == 1 && !s->ep_exact);
+    if (!classify) {
+      const unsigned long long w0 = s->h_st.stats[SS_WRITERS];
+      if ((rc = stitch_run_ordered(s, nullptr, r, r + m, false, true, nullptr))) return rc;
+      const unsigned long long writers = s->h_st.stats[SS_WRITERS] - w0;
+      s->ep.exact_epochs++; s->ep.exact_runs += m;
+      s->ep_size = (uint32_t)std::min<uint64_t>((uint64_t)s->ep_size * 2, g.epoch_max);
+      if (writers * 100 < (unsigned long long)m * g.epoch_switch_pct) s->ep_exact = false;
+    } else {
+      uint32_t n_exact = 0;
+      if ((rc = stitch_epoch_classify(s, r, m, &n_exact))) return rc;
+      s->ep.classify_epochs++; s->ep.dry_records += m;
+      // the exact set grows with the epoch (every write taints the later records of the epoch that share its slot)
+      if ((uint64_t)n_exact * 2 > m) { s->ep_exact = true; s->ep_size = std::max<uint32_t>(s->ep_size / 2, g.epoch0); }
+      else if ((uint64_t)n_exact * 100 > (uint64_t)m * g.epoch_shrink_pct) s->ep_size = std::max<uint32_t>(s->ep_size / 2, g.epoch0);
+      else if ((uint64_t)n_exact * 100 < (uint64_t)m * g.epoch_grow_pct) s->ep_size = (uint32_t)std::min<uint64_t>((uint64_t)s->ep_size * 2, g.epoch_max);
+    }
+    r += m;
+  }
   if (want_ext) {
-    unsigned long long used = 0;
-    CU(cudaMemcpy(&used, &s->d_st->ext_used, 8, cudaMemcpyDeviceToHost));
-    size_t at = s->h_ext.size();
-    s->h_ext.resize(at + used);
-    if (used) CU(cudaMemcpy(s->h_ext.data() + at, s->d_ext, used * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMemsetAsync(&s->d_st->ext_used, 0, 8, s->stream));
+    if ((rc = stitch_drain_ext(s))) return rc;
     s->lpf.process_batch(s->h_ext.data(), s->h_ext.size(), s->n_recs, s->rec_base);
   }
   s->rec_base += s->n_recs;
@@ -948,6 +1104,9 @@ static int stitch_finish(faucet_session* s) {
   g.tim.stitch_rounds = st.stats[SS_ROUNDS];
   g.tim.stitch_deferred = st.stats[SS_DEFERRED];
   for (int i = 0; i < 8; i++) g.tim.stitch_phase_ns[i] = st.stats[SS_T_PHASE1 + i];
+  g.tim.epochs_exact = s->ep.exact_epochs; g.tim.epochs_classify = s->ep.classify_epochs;
+  g.tim.exact_records = s->ep.exact_runs; g.tim.dry_records = s->ep.dry_records; g.tim.epoch_iterations = s->ep.iterations;
+  g.tim.epoch_fallbacks = s->ep.fallbacks; g.tim.nonquiet_records = s->ep.nonquiet; g.tim.writer_records = st.stats[SS_WRITERS];
   return 0;
 }
 
@@ -1441,6 +1600,7 @@ int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int
   if (!s || !s->retained_valid || s->k != k || s->log2_tai != log2_tai || s->n_hash != n_hash)
     return fail(FAUCET_E_STATE, "no retained planes for this geometry: run faucet_gpu_load_two_filters_mem with the "
                                 "\"retain_planes\" tuning set (and within \"retain_budget\"), or use faucet_gpu_scan_mem");
+  if (s->j != j) s->memo_dirty = true;  // the depth of the j-check is part of what the memo holds
   s->j = j; s->max_spacer = max_spacer_dist;
   int rc;
   if ((rc = ensure_scan_buffers(s))) return rc;

@@ -49,8 +49,7 @@ struct ScanArgs {
   uint64_t memo_mask;        // entries - 1 (power of two, >= 2^20)
   int memo_qbits;            // 64 - log2(entries): bits of the hash kept in the entry
   unsigned long long* dbg;   // optional counters: [0] lanes that missed, [1] warp passes through the long path, [2] failed inserts
-  uint8_t* flags;     // one byte per byte offset (warp-per-record stitch) ...
-  uint32_t* fplanes;  // ... or, when not NULL, the same bits transposed: word w of plane i (= bit i) at fplanes[8 w + i]
+  uint8_t* flags;     // one byte per byte offset
 };
 
 // Word holding bit (h mod tai).  Hash values are carried UNMASKED: (h0 + i*h1) mod tai only needs the
@@ -143,7 +142,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_ker
     const uint64_t win = inval_window(lo, hi, lane);
     const bool start_ok = (win & kbits) == 0;
     if (!__any_sync(0xffffffffu, start_ok)) {
-      if (a.fplanes && lane < 8) a.fplanes[(size_t)w * 8 + lane] = 0u;
       continue;
     }
     const uint32_t p = (w << 5) + lane;
@@ -263,16 +261,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_ker
         }
         f |= d == 0 ? (junc << 1) | (cnt << 3) : (junc << 2) | (cnt << 5);
       }
-      if (!a.fplanes) a.flags[p] = (uint8_t)f;
-    }
-    if (a.fplanes) {  // 7 ballots transpose the warp's 32 flag bytes into one 32-byte group of plane words
-      uint32_t mine = 0;
-#pragma unroll
-      for (int i = 0; i < 7; i++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, (f >> i) & 1u);
-        if (lane == i) mine = b;
-      }
-      if (lane < 8) a.fplanes[(size_t)w * 8 + lane] = mine;
+      a.flags[p] = (uint8_t)f;
     }
     __syncwarp();  // the queues are reused by the next word
   }
@@ -352,7 +341,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
     const uint64_t win = inval_window(lo, hi, lane);
     const bool start_ok = (win & kbits) == 0;
     if (!__any_sync(0xffffffffu, start_ok)) {
-      if (a.fplanes && lane < 8) a.fplanes[(size_t)w * 8 + lane] = 0u;
       continue;
     }
     const uint64_t fwd_raw = kmer_at(a.packed, p, k);
@@ -506,17 +494,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
       const uint32_t jb = has_prev ? jlut[mb | (real_b << 8)] : 0u;
       f = 1u | ((jf & 1u) << 1) | ((jb & 1u) << 2) | ((jf >> 1) << 3) | ((jb >> 1) << 5);
     }
-    if (a.fplanes) {
-      uint32_t mine = 0;
-#pragma unroll
-      for (int i = 0; i < 7; i++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, (f >> i) & 1u);
-        if (lane == i) mine = b;
-      }
-      if (lane < 8) a.fplanes[(size_t)w * 8 + lane] = mine;
-    } else if (start_ok) {
-      a.flags[p] = (uint8_t)f;
-    }
+    if (start_ok) a.flags[p] = (uint8_t)f;
   }
 }
 

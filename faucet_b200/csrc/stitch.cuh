@@ -30,9 +30,24 @@
 // updates are commutative (dist = max, cov = count, linked = or) and are issued as fire-and-forget
 // atomics; what later records READ is ordered by the rounds.
 //
+// Epochs.  After the first few x coverage almost every record is QUIET: it creates no
+// junction, raises no stored distance, sets no new link -- it only counts coverage, which nothing reads.
+// The stream is therefore cut into epochs.  An epoch either runs entirely through the ordered kernel above
+// (dense phase), or:
+//   classify  every record walks READ-ONLY against the table as it stood when the epoch began (T0), fully
+//             parallel, no ordering (stitch_dry_kernel); the ones that would write form the exact set E;
+//   execute   E runs through the ordered kernel, in stream order, on the live table; every real write
+//             (creation / raised distance) marks dirty[minimizer slot of that k-mer] = min(record);
+//   verify    a record outside E whose line touches a slot written by an EARLIER record may have seen a
+//             stale T0: it joins E, the table is restored to T0 and E runs again -- until nothing joins;
+//   apply     the records outside E (quiet under T0, and T0 is what they would have seen) add their
+//             coverage counts, again fully parallel, reading T0 (stitch_dry_kernel).
+// By induction over the stream every record outside E behaves exactly as in the sequential run (its keys are
+// untouched before its turn), so E -- executed in order from T0 -- sees exactly the sequential state.
+//
 // The junction map is an open-addressing table in HBM: key = oriented k-mer (ReadKmer::getKmer),
 // 64-byte record of u32 fields (dist[5], linked mask, cov[4] counts), 8-byte creation stamp =
-// (record index, n-th creation in that record).  Sorting by stamp gives the reference's creation
+// (record index << STAMP_SHIFT | n-th creation in that record).  Sorting by stamp gives the reference's creation
 // order; cov saturates at 255 when the map is collected (utils/Junction.cpp:59-67).
 #pragma once
 #include <cooperative_groups.h>
@@ -59,10 +74,22 @@ constexpr int RES_CAP = 96;     // reservation slots per line kept in shared mem
 constexpr int VIS_CAP = 32;     // junction slots a line touched (beyond it every skip distance is re-read)
 constexpr int REC_WORDS = 16;   // u32 per junction record
 enum { REC_DIST = 0, REC_LINK = 5, REC_COV = 6 };
+constexpr int STAMP_SHIFT = 26; // creation stamp = record index << 26 | n-th creation of that record (a line is < 2^24 bytes)
+constexpr unsigned long long STAMP_LOW = (1ull << STAMP_SHIFT) - 1ull;
+constexpr int LAND_CAP = 160;   // junctions one line may land on in the read-only walk (more: the ordered kernel takes it)
+constexpr int DRY_THREADS = 256;
+constexpr int DRY_WARPS = DRY_THREADS / 32;
+enum { DRY_CLASSIFY = 0, DRY_APPLY = 1 };
 
 enum { ST_DONE = 0, ST_GROW_TABLE = 1, ST_DRAIN_EXT = 2, ST_MORE_ROWS = 3, ST_STUCK = 4 };
 enum { SS_JCHECK = 0, SS_NOJUNC, SS_PROCESSED, SS_SKIPPED, SS_NOERR, SS_UNAMBIG, SS_ROUNDS, SS_DEFERRED,
-       SS_T_PHASE1, SS_T_SYNC1, SS_T_PHASE2, SS_T_SYNC2, SS_T_P1A, SS_T_P1B, SS_T_P1C, SS_T_P2A, SS_COUNT };  // SS_T_*: ns seen by warp 0 of the grid
+       SS_T_PHASE1, SS_T_SYNC1, SS_T_PHASE2, SS_T_SYNC2, SS_T_P1A, SS_T_P1B, SS_T_P1C, SS_T_P2A,  // SS_T_*: ns seen by warp 0 of the grid
+       SS_WRITERS,    // records the ordered kernel ran that wrote something a later record can see (or a new link)
+       SS_NONQUIET,   // records the read-only walk handed to the ordered kernel
+       SS_TAINTED,    // records the verify step added to the exact set
+       SS_DRY_ERROR,  // apply found a record that is not quiet (must stay 0)
+       SS_COUNT };
+constexpr int SS_WALK = 6;      // the first six are the reference's scan counters; a read-only walk holds them per record
 
 struct StitchState {             // device-resident; survives kernel launches and batches
   unsigned long long n_entries;  // occupied slots of the junction table
@@ -75,21 +102,16 @@ struct StitchState {             // device-resident; survives kernel launches an
   unsigned int round;
   unsigned int status;
   unsigned int special;          // the key equal to KEY_EMPTY (k = 32, all 'G') is present
-  unsigned int nb[3];            // stitch2: readers newly blocked in fix-point iteration i mod 3
-  unsigned int min_w[2];         // stitch2: smallest writer of the round (by round parity); stale values only err low
-  unsigned long long quiet_runs; // stitch2: records executed as readers
 };
 
 struct StitchArgs {
   const uint32_t* inval;
   const uint32_t* packed;
-  const uint8_t* flags;           // scan_flags output, one byte per k-mer start (warp-per-record kernel) ...
-  const uint32_t* fplanes;        // ... or the same bits as 8 interleaved planes (thread-per-record kernel, stitch2.cuh)
-  const uint32_t* rows;           // stitch2: reservation slots of record r at rows[32 (r - row_base)] (count, then slots)
-  uint32_t row_base, row_end;     // stitch2: records [row_base, row_end) have rows
+  const uint8_t* flags;           // scan_flags output, one byte per k-mer start
   const uint32_t* seq_start;
   const uint32_t* seq_end;
-  uint32_t n_recs;               // records in this batch
+  uint32_t n_recs;               // ordered kernel: it runs the entries [st->next, n_recs) ...
+  const uint32_t* list;          // ... of this ascending list of record indices (NULL: the record indices themselves)
   unsigned long long rec_base;   // global index of record 0 of this batch
   int k, j, spacer;
   int no_cleaning, paired;
@@ -98,10 +120,17 @@ struct StitchArgs {
   unsigned long long* stamps;
   unsigned long long cap;        // power of two, < 2^31
   uint32_t* res;                 // reservation table
-  uint32_t* resw;                // stitch2: the same slots, reserved by writers only (reader / writer scheme)
   uint32_t res_mask;
+  uint32_t* dirty;               // same slots: smallest record index that wrote a junction whose k-mer has that minimizer
+                                 // (ordered kernel marks, verify reads; NULL outside classify epochs)
+  // read-only walk (stitch_dry_kernel / stitch_verify_kernel): keys/recs above are the epoch's T0 snapshot
+  uint32_t* cov_out;             // records of the LIVE table: apply adds the coverage counts here (same slots as T0)
+  uint8_t* in_exact;             // per record of the batch: 1 = member of the exact set
+  uint32_t r_begin, r_end;       // the epoch
+  int dry_mode;
   uint32_t* deferred[2];         // w_max entries each
   StitchState* st;
+  const unsigned int* special;   // "the KEY_EMPTY k-mer is present" of the table behind keys (the live state's or the snapshot's)
   uint32_t* spf;                 // short pair filter on the device (NULL: none)
   unsigned long long spf_mask;
   int spf_nh;
@@ -154,25 +183,31 @@ __device__ __forceinline__ uint32_t code_at_t(const uint32_t* packed, uint32_t p
   return (ldw<SH>(packed + (p >> 4)) >> (30 - 2 * (p & 15))) & 3u;
 }
 
-// scan_flags byte of byte offset p, from whichever form the batch holds (plane i = bit i of the byte)
-__device__ __forceinline__ uint32_t flag_byte(const StitchArgs& a, uint32_t p) {
-  if (a.flags) return a.flags[p];
-  const uint32_t* w = a.fplanes + (size_t)(p >> 5) * 8;
-  uint32_t f = 0;
-#pragma unroll
-  for (int i = 0; i < 7; i++) f |= ((__ldg(w + i) >> (p & 31)) & 1u) << i;
-  return f;
-}
+__device__ __forceinline__ uint32_t flag_byte(const StitchArgs& a, uint32_t p) { return a.flags[p]; }
 
-// h(canonical s-mer starting at byte offset q), s <= 16
-template <bool SH>
-__device__ __forceinline__ uint32_t smer_hash(const uint32_t* packed, uint32_t q, int s) {
-  uint32_t w0 = ldw<SH>(packed + (q >> 4)), w1 = ldw<SH>(packed + (q >> 4) + 1);
-  uint32_t x = __funnelshift_l(w1, w0, 2 * (q & 15)) >> (32 - 2 * s);
+// h(canonical s-mer), s <= 16; x = the s-mer, first base in the high bits of its 2s-bit value
+__device__ __forceinline__ uint32_t smer_canon_hash(uint32_t x, int s) {
   uint32_t r = __brev(x << (32 - 2 * s));                       // reversed bit order, low-aligned
   r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);      // un-swap inside the 2-bit groups
   r ^= (s == 16 ? 0xaaaaaaaau : (0xaaaaaaaau & ((1u << (2 * s)) - 1u)));
   return mix32(x < r ? x : r);
+}
+// the s-mer starting at byte offset q
+template <bool SH>
+__device__ __forceinline__ uint32_t smer_hash(const uint32_t* packed, uint32_t q, int s) {
+  uint32_t w0 = ldw<SH>(packed + (q >> 4)), w1 = ldw<SH>(packed + (q >> 4) + 1);
+  return smer_canon_hash(__funnelshift_l(w1, w0, 2 * (q & 15)) >> (32 - 2 * s), s);
+}
+// reservation slot of ONE k-mer given by value (either orientation gives the same slot): the minimum over
+// its k-s+1 <= 17 s-mers, one per lane.  Equals what line_reservations finds for that k-mer inside a line.
+__device__ __forceinline__ uint32_t kmer_res_slot(uint64_t key, int k, uint32_t res_mask, int lane) {
+  const int s = k < 16 ? k : 16, w = k - s + 1;
+  uint32_t h = 0xffffffffu;
+  if (lane < w) {
+    const uint32_t x = (uint32_t)(key >> (2 * (k - s - lane))) & (s == 16 ? 0xffffffffu : ((1u << (2 * s)) - 1u));
+    h = smer_canon_hash(x, s);
+  }
+  return __reduce_min_sync(0xffffffffu, h) & res_mask;
 }
 
 // value at position lane+d of the 64-entry sequence (x0 = entries 0..31, x1 = entries 32..63)
@@ -238,7 +273,7 @@ __device__ bool line_reservations(const StitchArgs& a, const uint32_t* packed, u
 
 // ---- junction table -----------------------------------------------------------------------------
 __device__ __forceinline__ int tbl_find(const StitchArgs& a, uint64_t key) {
-  if (key == KEY_EMPTY) return __ldcg(&a.st->special) ? (int)a.cap : -1;
+  if (key == KEY_EMPTY) return __ldcg(a.special) ? (int)a.cap : -1;
   uint64_t h = mix64(key) & (a.cap - 1);
   while (true) {
     unsigned long long kk = __ldcg(a.keys + h);
@@ -307,7 +342,10 @@ __device__ void spf_add_pair(const StitchArgs& a, uint64_t k1, uint64_t k2) {
 
 struct WarpCtx {
   unsigned long long stamp;         // next creation stamp of the current record
-  WarpScratch* S;
+  WarpScratch* S;                   // lookups parked by phase 1 (ordered kernel, lines that fit POS_CAP)
+  unsigned long long* stage;        // EXT_STAGE staged real-extension k-mers
+  unsigned long long* cnt;          // where the walk's scan counters go (lane 0): the warp's totals, or -- in the
+                                    // read-only walk -- the record's own, added to the totals only if it commits
   uint32_t ls;                      // byte offset of the current line
   const uint32_t* pk;               // 2-bit plane as the walk sees it (shared copy or global) ...
   uint32_t pk_base;                 // ... and the byte offset of its word 0
@@ -316,6 +354,12 @@ struct WarpCtx {
   int n_pos;                        // k-mer positions of the line held in S (0: direct path)
   int n_vis;                        // entries of S->visited (> VIS_CAP: overflowed)
   uint32_t n_stage, part, rec;
+  bool wrote;                       // ordered kernel: the record changed something a later record can see, or set a link
+  // read-only walk
+  uint32_t* land_slot;              // junction slots the line landed on ...
+  uint8_t* land_nt;                 // ... and the real next nucleotide there (coverage index)
+  int n_land;
+  bool emit;                        // side effects on (pair filter adds, extension lists): apply, never classify
 };
 
 __device__ void ext_flush(const StitchArgs& a, WarpCtx& c, int lane) {
@@ -326,10 +370,40 @@ __device__ void ext_flush(const StitchArgs& a, WarpCtx& c, int lane) {
   off = __shfl_sync(0xffffffffu, off, 0);
   if (lane == 0) a.ext[off] = ((unsigned long long)c.rec << 32) | ((unsigned long long)(c.part & 0xffffu) << 16) | n;
   __syncwarp();
-  if (lane < (int)n) a.ext[off + 1 + lane] = c.S->stage[lane];
+  if (lane < (int)n) a.ext[off + 1 + lane] = c.stage[lane];
   __syncwarp();
   c.n_stage = 0;
   c.part++;
+}
+
+// the result list of one valid sub-read (scan_forward's `result`, src/ReadScanner.cpp:146) as far as the pair filters need it
+struct OutList {
+  uint64_t v_prev1 = 0, v_prev2 = 0, fb_ext = 0, lf_ext = 0;  // v[n-1], v[n-2]; first backward / last forward extension
+  uint32_t n_out = 0;
+  int rev_pos = 0, for_pos = 0;
+  bool have_fb = false, have_lf = false;
+};
+// dir: 0 / 1 = the junction faces backward / forward, -1 = the fake mid-read junction (:198-201)
+__device__ __forceinline__ void out_push(const StitchArgs& a, WarpCtx& c, OutList& o, uint64_t real_ext, int dir, int pos,
+                                         bool pairs, bool want_ext, int lane) {
+  if (dir == 0) { if (!o.have_fb) { o.have_fb = true; o.fb_ext = real_ext; o.rev_pos = pos; } }
+  else if (dir == 1) { if (!o.have_lf) { o.have_lf = true; o.for_pos = pos; } o.lf_ext = real_ext; }
+  // pairs (v[i], v[i+2]) once the list has more than two entries; a list that ends with exactly two
+  // entries is handled by out_finish (:208-225)
+  if (pairs && o.n_out >= 2 && lane == 0) spf_add_pair(a, o.v_prev2, real_ext);
+  o.v_prev2 = o.v_prev1; o.v_prev1 = real_ext; o.n_out++;
+  if (want_ext) {
+    if (lane == 0) c.stage[c.n_stage] = real_ext;
+    c.n_stage++;
+    __syncwarp();
+    if (c.n_stage == EXT_STAGE - 1) ext_flush(a, c, lane);
+  }
+}
+__device__ __forceinline__ void out_finish(const StitchArgs& a, const OutList& o, bool pairs, int lane) {
+  if (pairs && o.n_out == 2 && lane == 0) {  // :208-218
+    if (o.have_fb && o.have_lf && !(o.rev_pos > o.for_pos)) spf_add_pair(a, o.fb_ext, o.lf_ext);
+    if (o.have_fb != o.have_lf) spf_add_pair(a, o.v_prev2, o.v_prev1);
+  }
 }
 
 // has this line already touched `slot`?  (then the skip distance parked in phase 1 may be stale)
@@ -352,6 +426,33 @@ __device__ __forceinline__ void line_publish(const StitchArgs& a, WarpCtx& c, ui
   }
   __syncwarp();
 }
+// epoch bookkeeping of the ordered kernel: a junction with this key was created or had a distance raised by `rec`
+__device__ __forceinline__ void mark_dirty(const StitchArgs& a, uint64_t key, uint32_t rec, int lane) {
+  const uint32_t slot = kmer_res_slot(key, a.k, a.res_mask, lane);
+  if (lane == 0) atomicMin(a.dirty + slot, rec);
+}
+
+// one lane: the junction updates of a landing.  Returns bit 0: this junction changed visibly (created / distance
+// raised), bit 1: the previous junction's distance was raised, bit 2: anything changed (links included).
+__device__ __forceinline__ uint32_t landing_updates(const StitchArgs& a, int slot, int real, int back_idx, bool created,
+                                                    bool have_last, int last_slot, int last_fwd_idx, int d, int first_len) {
+  uint32_t wr = created ? 5u : 0u;
+  rec_add_cov(a, slot, real);
+  if (have_last) {  // directLinkJunctions (utils/JunctionMap.cpp:551-561)
+    const uint32_t dv = (uint32_t)d & 0xffu;
+    const uint32_t o1 = atomicMax(rec_field(a, last_slot, REC_DIST + last_fwd_idx), dv);
+    const uint32_t o2 = atomicOr(rec_field(a, last_slot, REC_LINK), 1u << last_fwd_idx);
+    const uint32_t o3 = atomicMax(rec_field(a, slot, REC_DIST + back_idx), dv);
+    const uint32_t o4 = atomicOr(rec_field(a, slot, REC_LINK), 1u << back_idx);
+    if (o1 < dv) wr |= 6u;
+    if (o3 < dv) wr |= 5u;
+    if (!((o2 >> last_fwd_idx) & 1u) || !((o4 >> back_idx) & 1u)) wr |= 4u;
+  } else {
+    const uint32_t dv = (uint32_t)first_len & 0xffu;
+    if (atomicMax(rec_field(a, slot, REC_DIST + back_idx), dv) < dv) wr |= 5u;
+  }
+  return wr;
+}
 
 // scan_forward (src/ReadScanner.cpp:112-231) on the valid sub-read at byte offset s0, `len` bases.
 // FAST: the line's lookups were parked in shared memory in phase 1 (c.S, index = s0 - c.ls + pos).
@@ -362,25 +463,12 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
   const int rel = (int)(s0 - c.ls);
   const int tested_end = 2 * len - 2 * k + 1 - 2 * j;  // distToEnd > 2j  <=>  tp < tested_end
   int tp = 2 * j + 1, last_junc_pos = 0;
-  bool have_last = false, have_fb = false, have_lf = false;
-  int last_tp = 0, last_fwd_idx = 0, rev_pos = 0, for_pos = 0, last_slot = -1;
-  uint64_t fb_ext = 0, lf_ext = 0, v_prev1 = 0, v_prev2 = 0;  // v[n-1], v[n-2] of this sub-read's result list
-  uint32_t n_out = 0;
+  bool have_last = false;
+  int last_tp = 0, last_fwd_idx = 0, last_slot = -1;
+  uint64_t last_key = 0;
+  OutList o;
   const bool pairs = !a.no_cleaning && a.spf != nullptr;
   const bool want_ext = a.ext != nullptr;
-
-  auto push_out = [&](uint64_t real_ext) {
-    // pairs (v[i], v[i+2]) once the list has more than two entries; a list that ends with exactly two
-    // entries is handled after the loop (:208-225)
-    if (pairs && n_out >= 2 && lane == 0) spf_add_pair(a, v_prev2, real_ext);
-    v_prev2 = v_prev1; v_prev1 = real_ext; n_out++;
-    if (want_ext) {
-      if (lane == 0) c.S->stage[c.n_stage] = real_ext;
-      c.n_stage++;
-      __syncwarp();
-      if (c.n_stage == EXT_STAGE - 1) ext_flush(a, c, lane);
-    }
-  };
 
   while (true) {
     // ---- find_next_junction (:61-86): 32 half-steps per warp iteration
@@ -415,15 +503,15 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       // NbJCheckKmer (:46): every half-step that reached testForJunction, the hit one included
       uint32_t jc = (active && ((upto >> lane) & 1u) && !known && !spc) ? cnt : 0u;
       jc = __reduce_add_sync(0xffffffffu, jc);
-      if (lane == 0) c.S->st[SS_JCHECK] += jc;
+      if (lane == 0) c.cnt[SS_JCHECK] += jc;
       if (hb) {
-        if (lane == 0) c.S->st[SS_PROCESSED] += hit;
+        if (lane == 0) c.cnt[SS_PROCESSED] += hit;
         tp += hit;
         slot = __shfl_sync(0xffffffffu, sl, hit);
         found = true;
         break;
       }
-      if (lane == 0) c.S->st[SS_PROCESSED] += __popc(am);
+      if (lane == 0) c.cnt[SS_PROCESSED] += __popc(am);
       tp += 32;
     }
     if (!found) break;
@@ -447,16 +535,8 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       if (FAST) line_publish(a, c, key, slot, lane);
     }
     const bool seen = line_visited(c, slot, lane);
-    if (lane == 0) {
-      rec_add_cov(a, slot, real);
-      if (have_last) {  // directLinkJunctions (utils/JunctionMap.cpp:551-561)
-        const int d = tp - last_tp;
-        rec_update(a, last_slot, last_fwd_idx, d); rec_link(a, last_slot, last_fwd_idx);
-        rec_update(a, slot, back_idx, d); rec_link(a, slot, back_idx);
-      } else {
-        rec_update(a, slot, back_idx, tp - 2 * j);
-      }
-    }
+    uint32_t wr = 0;
+    if (lane == 0) wr = landing_updates(a, slot, real, back_idx, created, have_last, last_slot, last_fwd_idx, tp - last_tp, tp - 2 * j);
     int dist;
     if (created) dist = 0;  // a zeroed record; back_idx != fwd_idx, so nothing written above shows here
     else if (FAST && known && !seen) dist = c.S->hop[2 * (rel + pos) + dir];
@@ -465,14 +545,19 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       dist = __shfl_sync(0xffffffffu, dist, 0);
     }
     if (dist < 1) dist = 1;
-    if (lane == 0) { c.S->st[SS_PROCESSED] += 1; c.S->st[SS_SKIPPED] += (unsigned long long)(dist - 1); }
+    if (lane == 0) { c.cnt[SS_PROCESSED] += 1; c.cnt[SS_SKIPPED] += (unsigned long long)(dist - 1); }
     line_visit(c, slot, lane);
-    const uint64_t real_ext = ext_fwd(key, (uint32_t)real, mask);
-    if (!dir) { if (!have_fb) { have_fb = true; fb_ext = real_ext; rev_pos = pos; } }
-    else { if (!have_lf) { have_lf = true; for_pos = pos; } lf_ext = real_ext; }
-    push_out(real_ext);
+    wr = __shfl_sync(0xffffffffu, wr, 0);
+    if (wr) {
+      c.wrote = true;
+      if (a.dirty) {
+        if (wr & 1u) mark_dirty(a, key, c.rec, lane);
+        if (wr & 2u) mark_dirty(a, last_key, c.rec, lane);
+      }
+    }
+    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
     have_last = true;
-    last_junc_pos = tp; last_tp = tp; last_slot = slot; last_fwd_idx = fwd_idx;
+    last_junc_pos = tp; last_tp = tp; last_slot = slot; last_fwd_idx = fwd_idx; last_key = key;
     tp += dist;
   }
   if (!have_last) {  // add_fake_junction (:92-104): mid-read, facing forward
@@ -481,29 +566,141 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
     const int real = (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base);
     int slot = 0;
     bool created = false;
+    uint32_t wr = 0;
     if (lane == 0) {
-      c.S->st[SS_NOJUNC]++;
+      c.cnt[SS_NOJUNC]++;
       slot = tbl_insert(a, key, &created);
-      if (created) a.stamps[slot] = c.stamp++;
+      if (created) { a.stamps[slot] = c.stamp++; wr = 1u; }
       rec_add_cov(a, slot, real);
       const int mtp = 2 * pos + 1;
-      rec_update(a, slot, 4, mtp - 2 * j);
-      rec_update(a, slot, real, (2 * len - mtp - 2 * k + 1) - 2 * j);
+      const uint32_t d4 = (uint32_t)(mtp - 2 * j) & 0xffu, dr = (uint32_t)((2 * len - mtp - 2 * k + 1) - 2 * j) & 0xffu;
+      if (atomicMax(rec_field(a, slot, REC_DIST + 4), d4) < d4) wr = 1u;
+      if (atomicMax(rec_field(a, slot, REC_DIST + real), dr) < dr) wr = 1u;
     }
     slot = __shfl_sync(0xffffffffu, slot, 0);
     created = __shfl_sync(0xffffffffu, (int)created, 0) != 0;
     c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
+    wr = __shfl_sync(0xffffffffu, wr, 0);
+    if (wr) { c.wrote = true; if (a.dirty) mark_dirty(a, key, c.rec, lane); }
     if (FAST && created) line_publish(a, c, key, slot, lane);
     line_visit(c, slot, lane);
-    push_out(ext_fwd(key, (uint32_t)real, mask));
-  } else if (lane == 0) {  // :205
-    rec_update(a, last_slot, last_fwd_idx, (2 * len - last_tp - 2 * k + 1) - 2 * j);
+    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
+  } else {  // :205
+    uint32_t wr = 0;
+    if (lane == 0) {
+      const uint32_t dv = (uint32_t)((2 * len - last_tp - 2 * k + 1) - 2 * j) & 0xffu;
+      wr = atomicMax(rec_field(a, last_slot, REC_DIST + last_fwd_idx), dv) < dv;
+    }
+    wr = __shfl_sync(0xffffffffu, wr, 0);
+    if (wr) { c.wrote = true; if (a.dirty) mark_dirty(a, last_key, c.rec, lane); }
   }
   __syncwarp();
-  if (pairs && n_out == 2 && lane == 0) {  // :208-218
-    if (have_fb && have_lf && !(rev_pos > for_pos)) spf_add_pair(a, fb_ext, lf_ext);
-    if (have_fb != have_lf) spf_add_pair(a, v_prev2, v_prev1);
+  out_finish(a, o, pairs, lane);
+}
+
+// The same walk READ-ONLY against the epoch's snapshot (a.keys / a.recs): returns false as soon as the sub-read
+// would create a junction, raise a stored distance or set a new link (then the record belongs to the ordered
+// kernel).  A quiet sub-read leaves its landings in c.land_* (coverage counts, added when the record commits),
+// its counters in c.cnt and, when c.emit, its pair-filter / extension-list side effects.
+__device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int len, int lane) {
+  const int k = a.k, j = a.j;
+  const uint64_t mask = kmer_mask(k);
+  const int tested_end = 2 * len - 2 * k + 1 - 2 * j;
+  int tp = 2 * j + 1, last_junc_pos = 0;
+  bool have_last = false;
+  int last_tp = 0, last_fwd_idx = 0;
+  uint32_t last_dist_fwd = 0, last_link = 0;
+  OutList o;
+  const bool pairs = c.emit && !a.no_cleaning && a.spf != nullptr;
+  const bool want_ext = c.emit && a.ext != nullptr;
+
+  auto land = [&](int slot, int real) -> bool {
+    if (c.n_land >= LAND_CAP) return false;
+    if (lane == 0) { c.land_slot[c.n_land] = (uint32_t)slot; c.land_nt[c.n_land] = (uint8_t)real; }
+    c.n_land++;
+    return true;
+  };
+  // dist[0..4] and the link mask of a junction, one word per lane 0..5 (one 32-byte sector of the record)
+  auto head = [&](int slot) -> uint32_t { return lane < 6 ? __ldg(a.recs + (size_t)slot * REC_WORDS + lane) : 0u; };
+
+  while (true) {
+    bool found = false;
+    int slot = -1;
+    while (tp < tested_end) {
+      const int t = tp + lane;
+      const bool active = t < tested_end;
+      bool known = false, spc = false, tst = false;
+      uint32_t cnt = 0;
+      int sl = -1;
+      if (active) {
+        const int pos = t >> 1, dir = t & 1;
+        const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
+        sl = tbl_find(a, dir ? fwd : revcomp(fwd, k));
+        const uint32_t f = flag_byte(a, s0 + pos);
+        known = sl >= 0;
+        spc = t - last_junc_pos >= 2 * a.spacer - 1;
+        cnt = dir ? (f >> 3) & 3u : (f >> 5) & 3u;
+        tst = dir ? (f & 2u) != 0 : (f & 4u) != 0;
+      }
+      const uint32_t am = __ballot_sync(0xffffffffu, active);
+      const uint32_t hb = __ballot_sync(0xffffffffu, active && (known || spc || tst));
+      const int hit = hb ? __ffs(hb) - 1 : 32;
+      const uint32_t upto = hit < 32 ? (hit == 31 ? 0xffffffffu : ((2u << hit) - 1u)) : am;
+      uint32_t jc = (active && ((upto >> lane) & 1u) && !known && !spc) ? cnt : 0u;
+      jc = __reduce_add_sync(0xffffffffu, jc);
+      if (lane == 0) c.cnt[SS_JCHECK] += jc;
+      if (hb) {
+        if (lane == 0) c.cnt[SS_PROCESSED] += hit;
+        tp += hit;
+        slot = __shfl_sync(0xffffffffu, sl, hit);
+        found = true;
+        break;
+      }
+      if (lane == 0) c.cnt[SS_PROCESSED] += __popc(am);
+      tp += 32;
+    }
+    if (!found) break;
+    if (slot < 0) return false;  // a junction would be created here
+    const int pos = tp >> 1, dir = tp & 1;
+    const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
+    const uint64_t key = dir ? fwd : revcomp(fwd, k);
+    const int real = dir ? (int)code_at_t<false>(a.packed, s0 + pos + k) : (int)nt_comp(code_at_t<false>(a.packed, s0 + pos - 1));
+    const int fwd_idx = dir ? real : 4, back_idx = dir ? 4 : real;
+    const uint32_t hd = head(slot);
+    const uint32_t d_fwd = __shfl_sync(0xffffffffu, hd, fwd_idx), d_back = __shfl_sync(0xffffffffu, hd, back_idx);
+    const uint32_t link = __shfl_sync(0xffffffffu, hd, REC_LINK);
+    if (have_last) {
+      const uint32_t dv = (uint32_t)(tp - last_tp) & 0xffu;
+      if (dv > last_dist_fwd || dv > d_back || !((last_link >> last_fwd_idx) & 1u) || !((link >> back_idx) & 1u)) return false;
+    } else if (((uint32_t)(tp - 2 * j) & 0xffu) > d_back) {
+      return false;
+    }
+    if (!land(slot, real)) return false;
+    const int dist = d_fwd < 1u ? 1 : (int)d_fwd;
+    if (lane == 0) { c.cnt[SS_PROCESSED] += 1; c.cnt[SS_SKIPPED] += (unsigned long long)(dist - 1); }
+    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
+    have_last = true;
+    last_junc_pos = tp; last_tp = tp; last_fwd_idx = fwd_idx; last_dist_fwd = d_fwd; last_link = link;
+    tp += dist;
   }
+  if (!have_last) {  // the fake mid-read junction must already be there, with distances at least as long
+    const int pos = len / 2 - k / 2;
+    const uint64_t key = kmer_at_t<false>(a.packed, s0 + pos, k);
+    const int real = (int)code_at_t<false>(a.packed, s0 + pos + k);
+    const int slot = tbl_find(a, key);
+    if (slot < 0) return false;
+    const uint32_t hd = head(slot);
+    const int mtp = 2 * pos + 1;
+    const uint32_t d4 = (uint32_t)(mtp - 2 * j) & 0xffu, dr = (uint32_t)((2 * len - mtp - 2 * k + 1) - 2 * j) & 0xffu;
+    if (d4 > __shfl_sync(0xffffffffu, hd, 4) || dr > __shfl_sync(0xffffffffu, hd, real)) return false;
+    if (!land(slot, real)) return false;
+    if (lane == 0) c.cnt[SS_NOJUNC]++;
+    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
+  } else if (((uint32_t)((2 * len - last_tp - 2 * k + 1) - 2 * j) & 0xffu) > last_dist_fwd) {
+    return false;
+  }
+  out_finish(a, o, pairs, lane);
+  return true;
 }
 
 // highest position in [s, pos) whose plane bit equals `want`, or -1; uniform across the warp
@@ -525,9 +722,10 @@ __device__ long long find_prev_bit(const uint32_t* plane, uint32_t s, uint32_t p
   }
 }
 
-// scanInputRead (:260-282) + getValidReads (:233-257) for the sequence line [ls, le)
-template <bool FAST>
-__device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t le, int lane) {
+// scanInputRead (:260-282) + getValidReads (:233-257) for the sequence line [ls, le).
+// DRY: the read-only walk; returns false when the line is not quiet (always true otherwise).
+template <bool FAST, bool DRY>
+__device__ bool scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t le, int lane) {
   const int k = a.k, j = a.j;
   uint32_t pos = le;
   while (pos > ls) {  // getUnambiguousReads hands the segments over LAST first (utils/Kmer.cpp:64-80)
@@ -540,7 +738,7 @@ __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
     pos = ss;
     const int L = (int)(ee - ss);
     if (L < k || L < k + 2 * j + 1) continue;
-    if (lane == 0) c.S->st[SS_UNAMBIG]++;
+    if (lane == 0) c.cnt[SS_UNAMBIG]++;
     // getValidReads: maximal runs of >= k Bloom-positive k-mers; npos is a virtual negative position
     const int npos = L - k + 1;
     int run_start = -1;
@@ -562,14 +760,16 @@ __device__ void scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
           bit += __ffs(x) - 1;
           const int run_len = base + bit - run_start;
           if (run_len >= k) {
-            scan_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane);
-            if (lane == 0) c.S->st[SS_NOERR]++;
+            if (DRY) { if (!dry_forward(a, c, ss + run_start, run_len + k - 1, lane)) return false; }
+            else scan_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane);
+            if (lane == 0) c.cnt[SS_NOERR]++;
           }
           run_start = -1;
         }
       }
     }
   }
+  return true;
 }
 
 // phase 1: everything the walk will want to know about the line, all loads in flight together
@@ -634,7 +834,9 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
   WarpCtx c;
   if (lane < SS_COUNT) S->st[lane] = 0;
   __syncwarp();
-  c.S = S; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0; c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0;
+  c.S = S; c.stage = S->stage; c.cnt = S->st; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0;
+  c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0; c.wrote = false;
+  c.land_slot = nullptr; c.land_nt = nullptr; c.n_land = 0; c.emit = true;
   uint32_t status = ST_DONE;
 
   while (true) {
@@ -654,7 +856,8 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
     int n_res = 0;
     bool fast = false;
     if (have) {
-      rec = gw < nd ? __ldcg(a.deferred[cur] + gw) : next + (gw - nd);
+      if (gw < nd) rec = __ldcg(a.deferred[cur] + gw);
+      else { const uint32_t idx = next + (gw - nd); rec = a.list ? __ldg(a.list + idx) : idx; }
       ls = __ldg(a.seq_start + rec);
       const uint32_t le = __ldg(a.seq_end + rec);
       len = le > ls ? le - ls : 0u;
@@ -670,7 +873,7 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
         line_reservations<0, true>(a, S->pk, ls & 15u, len, rec, lane, S->reskey, &n_res);
         const unsigned long long tb = gtime_ns();
         prefetch_line<(MIN_BLOCKS >= 4 ? 1 : 2)>(a, S, ls, n_pos, lane);
-        if (gw == 0 && lane == 0) { c.S->st[SS_T_P1A] += ta - t0; c.S->st[SS_T_P1B] += tb - ta; c.S->st[SS_T_P1C] += gtime_ns() - tb; }
+        if (gw == 0 && lane == 0) { S->st[SS_T_P1A] += ta - t0; S->st[SS_T_P1B] += tb - ta; S->st[SS_T_P1C] += gtime_ns() - tb; }
       } else {
         line_reservations<0, false>(a, a.packed, ls, len, rec, lane, S->reskey, &n_res);
       }
@@ -699,41 +902,129 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
         mine = line_reservations<1, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
         line_reservations<2, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
       }
-      if (gw == 0 && lane == 0) c.S->st[SS_T_P2A] += gtime_ns() - t2;
+      if (gw == 0 && lane == 0) S->st[SS_T_P2A] += gtime_ns() - t2;
       if (mine) {
-        c.rec = rec; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls;
-        c.stamp = (a.rec_base + rec) << 20;
+        c.rec = rec; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls; c.wrote = false;
+        c.stamp = (a.rec_base + rec) << STAMP_SHIFT;
         if (fast) {
           c.n_pos = (int)(len - a.k + 1);
           c.pk = S->pk; c.pk_base = ls & ~15u; c.inv = S->inv; c.inv_base = ls & ~31u;
-          scan_line<true>(a, c, ls, ls + len, lane);
+          scan_line<true, false>(a, c, ls, ls + len, lane);
         } else if (len) {
           c.n_pos = 0;
           c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0;
-          scan_line<false>(a, c, ls, ls + len, lane);
+          scan_line<false, false>(a, c, ls, ls + len, lane);
         }
         if (a.ext && c.n_stage) ext_flush(a, c, lane);
+        if (c.wrote && lane == 0) S->st[SS_WRITERS]++;
       } else if (lane == 0) {
         a.deferred[nxt][atomicAdd(&st->nd[nxt], 1u)] = rec;
-        c.S->st[SS_DEFERRED]++;
+        S->st[SS_DEFERRED]++;
       }
     }
     const unsigned long long t3 = gtime_ns();
     grid.sync();
     if (gw == 0 && lane == 0) {
-      c.S->st[SS_T_PHASE1] += t1 - t0; c.S->st[SS_T_SYNC1] += t2 - t1; c.S->st[SS_T_PHASE2] += t3 - t2; c.S->st[SS_T_SYNC2] += gtime_ns() - t3;
+      S->st[SS_T_PHASE1] += t1 - t0; S->st[SS_T_SYNC1] += t2 - t1; S->st[SS_T_PHASE2] += t3 - t2; S->st[SS_T_SYNC2] += gtime_ns() - t3;
     }
     const uint32_t nd_next = __ldcg(&st->nd[nxt]);
     if (nd_next * a.shrink_den > n_win) W = W / 2 > a.w_min ? W / 2 : a.w_min;
     else if (nd_next * a.grow_den < n_win && n_win >= W) W = W * 2 < a.w_max ? W * 2 : a.w_max;
     next += n_new;
     round++;
-    if (gw == 0 && lane == 0) c.S->st[SS_ROUNDS]++;
+    if (gw == 0 && lane == 0) S->st[SS_ROUNDS]++;
   }
   __syncwarp();
   if (lane < SS_COUNT && S->st[lane]) atomicAdd(&st->stats[lane], S->st[lane]);
   if (gw == 0 && lane == 0) {
     __stcg(&st->next, next); __stcg(&st->W, W); __stcg(&st->round, round); __stcg(&st->status, status);
+  }
+}
+
+// ---- epochs: the read-only walk, the verify step, the exact-set list ------------------------------
+struct DryScratch {  // shared memory of one warp of the read-only kernels
+  unsigned long long stage[EXT_STAGE];
+  unsigned long long st[SS_COUNT];   // the warp's totals, flushed when the kernel ends
+  unsigned long long cnt[SS_WALK];   // the current record's counters
+  uint32_t land_slot[LAND_CAP];
+  uint8_t land_nt[LAND_CAP];
+};
+
+// DRY_CLASSIFY: every record of [r_begin, r_end) walks against the snapshot; in_exact[rec] := 1 when it is not quiet.
+// DRY_APPLY:    the records with in_exact == 0 walk again (same snapshot, same walk) and commit: coverage counts into
+//               the live table, scan counters, pair-filter adds and extension lists.
+__global__ void __launch_bounds__(DRY_THREADS) stitch_dry_kernel(StitchArgs a) {
+  __shared__ DryScratch scratch[DRY_WARPS];
+  DryScratch* S = scratch + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * DRY_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * DRY_THREADS) >> 5;
+  if (lane < SS_COUNT) S->st[lane] = 0;
+  __syncwarp();
+  WarpCtx c;
+  c.S = nullptr; c.stage = S->stage; c.cnt = S->cnt; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0;
+  c.n_pos = 0; c.n_vis = 0; c.stamp = 0; c.wrote = false; c.land_slot = S->land_slot; c.land_nt = S->land_nt;
+  c.emit = a.dry_mode == DRY_APPLY;
+  for (uint32_t rec = a.r_begin + gw; rec < a.r_end; rec += n_warps) {
+    if (a.dry_mode == DRY_APPLY && a.in_exact[rec]) continue;
+    const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
+    if (le <= ls) continue;
+    c.rec = rec; c.part = 0; c.n_stage = 0; c.n_land = 0; c.ls = ls;
+    if (lane < SS_WALK) S->cnt[lane] = 0;
+    __syncwarp();
+    const bool quiet = scan_line<false, true>(a, c, ls, le, lane);
+    __syncwarp();
+    if (a.dry_mode == DRY_CLASSIFY) {
+      if (!quiet && lane == 0) { a.in_exact[rec] = 1; S->st[SS_NONQUIET]++; }
+      continue;
+    }
+    if (!quiet) {  // cannot happen: apply repeats the walk classify found quiet
+      if (lane == 0) S->st[SS_DRY_ERROR]++;
+      c.n_stage = 0;
+      continue;
+    }
+    for (int i = lane; i < c.n_land; i += 32)
+      atomicAdd(a.cov_out + (size_t)S->land_slot[i] * REC_WORDS + REC_COV + S->land_nt[i], 1u);
+    if (lane < SS_WALK) S->st[lane] += S->cnt[lane];
+    if (a.ext && c.n_stage) ext_flush(a, c, lane);
+  }
+  __syncwarp();
+  if (lane < SS_COUNT && S->st[lane]) atomicAdd(&a.st->stats[lane], S->st[lane]);
+}
+
+// A record outside the exact set whose line touches a slot that an EARLIER record wrote joins the set.
+__global__ void __launch_bounds__(DRY_THREADS) stitch_verify_kernel(StitchArgs a) {
+  __shared__ uint32_t keep_s[DRY_WARPS][RES_CAP];
+  uint32_t* keep = keep_s[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * DRY_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * DRY_THREADS) >> 5;
+  unsigned long long added = 0;
+  for (uint32_t rec = a.r_begin + gw; rec < a.r_end; rec += n_warps) {
+    if (a.in_exact[rec]) continue;
+    const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
+    if (le <= ls || le - ls < (uint32_t)a.k) continue;
+    int n = 0;
+    line_reservations<3, false>(a, a.packed, ls, le - ls, rec, lane, keep, &n);
+    __syncwarp();
+    bool hit = n > RES_CAP;  // (a line with more slots than fit is taken by the ordered kernel)
+    for (int i = lane; i < n && i < RES_CAP; i += 32)
+      if (__ldcg(a.dirty + keep[i]) < rec) hit = true;
+    hit = __any_sync(0xffffffffu, hit);
+    if (hit && lane == 0) { a.in_exact[rec] = 1; added++; }
+    __syncwarp();
+  }
+  if (lane == 0 && added) atomicAdd(&a.st->stats[SS_TAINTED], added);
+}
+
+// in_exact flags of [r_begin, r_end) -> 0/1 counts (then exclusive prefix sum, then the ascending list)
+__global__ void exact_flags_kernel(const uint8_t* __restrict__ in_exact, uint32_t r_begin, uint32_t n, uint32_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in_exact[r_begin + i] ? 1u : 0u;
+}
+__global__ void exact_list_kernel(const uint8_t* __restrict__ in_exact, uint32_t r_begin, uint32_t n,
+                                  const uint32_t* __restrict__ prefix, uint32_t* __restrict__ list, uint32_t* __restrict__ count_out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool in = in_exact[r_begin + i] != 0;
+    if (in) list[prefix[i]] = r_begin + i;
+    if (i == n - 1) *count_out = prefix[i] + (in ? 1u : 0u);
   }
 }
 
@@ -765,7 +1056,7 @@ struct JunctionOut {  // == faucet_junction_rec (include/faucet_gpu.h)
   unsigned long long rank;
 };
 
-// Creation order without a sort: stamp = (record index << 20 | n-th creation of that record), and the
+// Creation order without a sort: stamp = (record index << STAMP_SHIFT | n-th creation of that record), and the
 // n-th creations of a record are dense, so  rank = (#junctions created by earlier records) + n.
 //   count:   hist[record]++ for every junction          scan: exclusive prefix sum of hist
 //   emit:    out[prefix[record] + n] = junction
@@ -774,7 +1065,7 @@ __global__ void stitch_count_kernel(const unsigned long long* __restrict__ keys,
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= cap;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const bool occ = i == cap ? special != 0 : keys[i] != KEY_EMPTY;
-    if (occ) atomicAdd(hist + (stamps[i] >> 20), 1u);
+    if (occ) atomicAdd(hist + (stamps[i] >> STAMP_SHIFT), 1u);
   }
 }
 
@@ -860,7 +1151,7 @@ __global__ void stitch_emit_kernel(const unsigned long long* __restrict__ keys, 
     const bool occ = i == cap ? special != 0 : key != KEY_EMPTY;
     if (!occ) continue;
     const unsigned long long stamp = stamps[i];
-    const unsigned long long rank = (unsigned long long)prefix[stamp >> 20] + (stamp & 0xfffffull);
+    const unsigned long long rank = (unsigned long long)prefix[stamp >> STAMP_SHIFT] + (stamp & STAMP_LOW);
     const uint32_t* r = recs + i * REC_WORDS;
     JunctionOut jo;
     jo.kmer = key;

@@ -55,6 +55,12 @@ typedef struct {
   uint64_t stitch_rounds, stitch_deferred; /* reservation rounds / deferred records of the last scan */
   uint64_t stitch_phase_ns[8];             /* ns in phase 1, barrier 1, phase 2, barrier 2, then phase-1 line fetch /
                                               reservations / lookups and phase-2 check (warp 0 of the grid) */
+  /* epochs of the last scan: epochs run entirely through the ordered kernel / through classify-execute-
+   * verify-apply; records the ordered kernel ran (re-runs included); records the read-only walk covered; ordered runs
+   * of exact sets (>= classify epochs with a non-empty set); epochs that fell back to the ordered kernel (table growth);
+   * records classified not quiet; records the ordered kernel found to have written */
+  uint64_t epochs_exact, epochs_classify, exact_records, dry_records, epoch_iterations, epoch_fallbacks,
+      nonquiet_records, writer_records;
 } faucet_timings;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
@@ -120,12 +126,14 @@ int faucet_gpu_set_batch_bytes(size_t bytes);
 int faucet_gpu_set_epoch_limit(uint64_t stamps);
 int faucet_gpu_get_timings(faucet_timings* out);
 /* Knobs (none changes a result; tests use them to force every code path).  Setting one drops the cached session.
- *  stitch:  "stitch_impl" 1 = one warp per record (default), 2 = lanes share the lookups and one thread walks a record,
- *           with reader/writer reservations; "table_cap0" initial junction-table slots (power of two, grows by rehash at
- *           load 1/2); "res_log2" log2 of the reservation-table entries; "stitch_w0" / "stitch_w_max" initial / maximal
- *           records per round; "stitch_shrink_den" / "stitch_grow_den" window adaptation; "stitch_blocks" resident CTAs
- *           per SM (2..4); "rows_max" records whose reservation rows are listed per launch (impl 2); "ext_cap0" u64
- *           words of the extension-list buffer that feeds the long pair filter
+ *  stitch:  "epoch_mode" 1 = adaptive epochs (default: ordered kernel while most records write, then read-only classify /
+ *           ordered exact set / verify / apply), 0 = one ordered run per batch, 2 = classify epochs from the first record;
+ *           "epoch0" / "epoch_max" first / largest epoch in records; "epoch_switch_pct", "epoch_shrink_pct",
+ *           "epoch_grow_pct" the thresholds of the epoch controller; "table_cap0" initial junction-table slots (power of
+ *           two, grows by rehash at load 1/2); "res_log2" log2 of the reservation-table entries; "stitch_w0" /
+ *           "stitch_w_max" initial / maximal records per round; "stitch_shrink_den" / "stitch_grow_den" window
+ *           adaptation; "stitch_blocks" resident CTAs per SM (2..4); "ext_cap0" u64 words of the extension-list buffer
+ *           that feeds the long pair filter
  *  scan:    "scan_memo" 1 = scan_flags caches the extension masks of every k-mer it has computed (default), 0 = every
  *           position from the Bloom filter; "memo_shift" cache entries = Bloom bits >> memo_shift (8 bytes each)
  *  load:    "load_sub_bytes0" / "load_sub_bytes" first / largest sub-batch of pass 1; "load_memo_log2" pass 1 caches
@@ -168,7 +176,7 @@ int faucet_session_timer_start(faucet_session* s);
 int faucet_session_timer_stop_ms(faucet_session* s, float* ms_out);
 uint64_t faucet_session_kernel_launches(faucet_session* s);
 /* event-timed duration (ms) accumulated per named kernel since the last reset:
- * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch */
+ * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch (ordered kernel) 5=stitch_dry (read-only walk, verify, exact-set list) */
 int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64_t* launches_out);
 
 /* ---- multi-GPU: one process per GPU of one NVSwitch box, peer HBM mapped through CUDA IPC -----

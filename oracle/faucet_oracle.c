@@ -10,6 +10,17 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* optional instrumentation for tools/exp/epoch_sim.c (never defined in the library build) */
+#ifdef FO_TRACE
+void fo_trace_write(uint64_t key, int kind);
+void fo_trace_record(void);
+#define TRACE_WRITE(key, kind) fo_trace_write(key, kind)
+#define TRACE_RECORD() fo_trace_record()
+#else
+#define TRACE_WRITE(key, kind) ((void)0)
+#define TRACE_RECORD() ((void)0)
+#endif
+
 /* ------------------------------------------------------------------ k-mer codec (utils/Kmer.cpp) */
 
 /* NT2int, utils/Kmer.cpp:82-88: A=0 C=1 T=2 G=3 */
@@ -332,6 +343,7 @@ static int64_t jmap_create(jmap_t* m, uint64_t key) {
   if (m->n == m->cap) { m->cap *= 2; m->recs = (fo_junction_rec*)realloc(m->recs, m->cap * sizeof(fo_junction_rec)); }
   memset(&m->recs[m->n], 0, sizeof(fo_junction_rec));
   m->recs[m->n].kmer = key;
+  TRACE_WRITE(key, 0);
   if ((m->n + 1) * 2 > m->nslots) {
     m->nslots *= 2; m->slots = (int64_t*)realloc(m->slots, m->nslots * sizeof(int64_t));
     for (uint64_t i = 0; i < m->nslots; i++) m->slots[i] = -1;
@@ -343,7 +355,7 @@ static int64_t jmap_create(jmap_t* m, uint64_t key) {
 /* Junction::update, utils/Junction.cpp:69-71; the int argument is narrowed to unsigned char at the call */
 static void junc_update(fo_junction_rec* r, int idx, int length) {
   uint8_t l = (uint8_t)length;
-  if (l > r->dist[idx]) r->dist[idx] = l;
+  if (l > r->dist[idx]) { r->dist[idx] = l; TRACE_WRITE(r->kmer, 1); }
 }
 /* Junction::addCoverage, utils/Junction.cpp:59-67 */
 static void junc_add_cov(fo_junction_rec* r, int nt) {
@@ -484,6 +496,8 @@ static void scan_forward(scanner_t* s, const char* read, int len, klist_t* out) 
       int e1 = cur_ext_index(&last_kmer, 1), e2 = cur_ext_index(&c, 0);
       int d = cur_total_pos(&c) - cur_total_pos(&last_kmer);
       junc_update(prev, e1, d); junc_update(junc, e2, d);
+      if (!prev->linked[e1]) TRACE_WRITE(prev->kmer, 2);
+      if (!junc->linked[e2]) TRACE_WRITE(junc->kmer, 2);
       prev->linked[e1] = 1; junc->linked[e2] = 1;
     } else {
       have_last = 1;
@@ -578,6 +592,7 @@ int fo_scan(const char* text, size_t n, int fastq, int paired_ends, int no_clean
     rd_getline(&rd, &read);
     klist_t* cur = first_end ? &b1 : &b2;
     cur->n = 0;
+    TRACE_RECORD();
     scan_input_read(&s, read, cur, &segs, &cap);
     if (paired_ends && !first_end && b1.n && b2.n && !no_cleaning && s.lpf) {
       for (size_t a = 0; a < b1.n; a++) {

@@ -14,7 +14,7 @@
 
 #include "../faucet_b200/csrc/kmer.cuh"
 #include "../faucet_b200/csrc/pair_filter_host.hpp"
-#include "../faucet_b200/csrc/stitch2_walk.cuh"
+#include "stitch2_walk.cuh"
 
 using namespace faucet;
 

@@ -12,12 +12,12 @@
 // one thread per record (instead of one warp) affordable.
 //
 // Everything here is __host__ __device__ and written against an environment type E, so the same code
-// runs in the CUDA kernel (DevEnv, stitch2.cuh) and in the CPU harness of the test-suite
+// TEST ASSET since round 2 (its CUDA kernel was retired): runs in the CPU harness of the test-suite
 // (tests/stitch2_host.cpp), where it is checked against the oracle.
 #pragma once
 #include <stdint.h>
 
-#include "kmer.cuh"
+#include "../faucet_b200/csrc/kmer.cuh"
 
 namespace faucet {
 

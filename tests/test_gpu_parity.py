@@ -42,12 +42,22 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
-@pytest.fixture(params=[1, 2], ids=["warp_per_record", "thread_walks_record"])
+EPOCH_DEFAULTS = {"epoch_mode": 1, "epoch0": 8192, "epoch_max": 1 << 20}
+EPOCH_SCHEDULES = {
+    "adaptive": {},                                                     # the default: ordered epochs first, then classify epochs
+    "ordered_only": {"epoch_mode": 0},                                  # one run of the ordered kernel per batch
+    "classify_tiny": {"epoch_mode": 2, "epoch0": 192, "epoch_max": 3000},  # classify / execute / verify / apply from record 0 on
+}
+
+
+@pytest.fixture(params=sorted(EPOCH_SCHEDULES))
 def impl(request, fb):
-    """both stitch kernels (faucet_b200/csrc/stitch.cuh, the default, and stitch2.cuh) are held to the same bar"""
-    fb.set_tuning("stitch_impl", request.param)
+    """every epoch schedule of the stitch (faucet_b200/csrc/stitch.cuh) is held to the same bar"""
+    for name, v in EPOCH_SCHEDULES[request.param].items():
+        fb.set_tuning(name, v)
     yield request.param
-    fb.set_tuning("stitch_impl", 1)
+    for name, v in EPOCH_DEFAULTS.items():
+        fb.set_tuning(name, v)
 
 
 def _geom(oracle, est, sing, fp=0.04):
@@ -190,7 +200,12 @@ def test_session_stage_api(fb, oracle, small_fq):
     {"stitch_w0": 1, "stitch_w_max": 1},                  # one record per round == plain sequential order
     {"stitch_w0": 32768, "stitch_w_max": 32768},          # window far larger than the genome supports
     {"table_cap0": 256, "ext_cap0": 256, "res_log2": 10, "stitch_w0": 512},
-    {"rows_max": 100, "stitch_w0": 64},                   # thread-per-record kernel: reservation rows listed 100 records at a time
+    {"epoch_mode": 2, "epoch0": 64, "epoch_max": 64},     # classify epochs of 64 records from the empty table on
+    {"epoch_mode": 2, "epoch0": 1 << 20},                 # ONE classify epoch per batch: the exact set closes over nearly everything
+    {"epoch_mode": 2, "epoch0": 1000, "table_cap0": 64},  # the table has to grow inside classify epochs (fallback to the ordered kernel)
+    {"epoch_mode": 2, "epoch0": 700, "ext_cap0": 64},     # extension lists drained inside the exact runs and between apply launches
+    {"epoch_mode": 2, "epoch0": 500, "res_log2": 8},      # every write taints most of the epoch (256 slots)
+    {"epoch_mode": 1, "epoch0": 256, "epoch_max": 4096, "epoch_switch_pct": 100},  # adaptive, switching to classify at once
     {"stitch_w0": 1 << 17, "stitch_w_max": 1 << 17},      # more window than the warp-per-record grid has warps
 ])
 def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs, impl):
@@ -205,7 +220,7 @@ def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs, impl):
     gspf, glpf = ospf.copy(), olpf.copy()
     orecs, ost = oracle.scan(text, True, True, 0, k, j, 100, b2, lt, nh, ospf, sg, olpf, lg)
     defaults = {"table_cap0": 1 << 22, "ext_cap0": 1 << 24, "res_log2": 24, "stitch_w0": 2048, "stitch_w_max": 1 << 15,
-                "rows_max": 1 << 22}
+                "epoch_switch_pct": 30, **EPOCH_DEFAULTS}
     try:
         for name, v in knobs.items():
             fb.set_tuning(name, v)
@@ -234,8 +249,8 @@ def test_stitch_repetitive_reads(fb, oracle, tmp_path_factory, impl):
 
 
 def test_stitch_mixed_line_lengths(fb, oracle, tmp_path_factory, impl):
-    """100 bp and 300 bp reads of one genome interleaved file-wise: the long lines (280 k-mer positions, more
-    reservation slots than a row holds) take the warp-cooperative path inside the thread-per-record kernel"""
+    """100 bp and 300 bp reads of one genome interleaved file-wise: the long lines (280 k-mer positions) take the
+    direct (not shared-memory staged) path of the ordered kernel"""
     _, short = _dataset(tmp_path_factory, "mix_s.fq", genome=30000, cov=15, length=100, insert=300, seed=21, err=0.005, nrate=0.002)
     _, long_ = _dataset(tmp_path_factory, "mix_l.fq", genome=30000, cov=15, length=300, insert=700, seed=21, err=0.005, nrate=0.002)
     a, b = short.split(b"\n")[:-1], long_.split(b"\n")[:-1]
@@ -387,3 +402,74 @@ def test_load_saturated_kmer_cache_is_invisible(fb, oracle, small_fq):
     finally:
         fb.set_tuning("load_memo_log2", 29)
         fb.set_batch_bytes(256 << 20)
+
+
+def test_scan_retained_j_change_clears_the_memo(fb, oracle, small_fq):
+    """the memo caches depth-j masks: scan_retained with bloo2 = None and another j must not reuse them"""
+    _, text = small_fq
+    k = 31
+    lt, nh = _geom(oracle, 100000, 50000)
+    _, o2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    try:
+        fb.set_tuning("retain_planes", 1)
+        fb.load_two_filters_mem(text, True, k, lt, nh)
+        for j in (1, 0, 2, 1):
+            orecs, ost = oracle.scan(text, True, True, 1, k, j, 100, o2, lt, nh)
+            grecs, gst = fb.scan_retained(True, 1, k, j, 100, None, lt, nh)
+            assert gst == ost and _strip(grecs) == _strip(orecs), j
+    finally:
+        fb.set_tuning("retain_planes", 0)
+
+
+@pytest.mark.parametrize("j", [3, 4])
+def test_scan_deep_jcheck(fb, oracle, tmp_path_factory, j):
+    """j = 3 and 4, the deepest the reference's JChecker scratch arrays allow (utils/JChecker.cpp:93-94)"""
+    _, text = _dataset(tmp_path_factory, "deep.fq", genome=20000, cov=25, length=100, insert=300, seed=31, err=0.01)
+    k, lt, nh = 25, 17, 2  # a full filter: many false-positive branches to chase
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    for memo in (1, 0):
+        try:
+            fb.set_tuning("scan_memo", memo)
+            orecs, ost = oracle.scan(text, True, True, 1, k, j, 100, b2, lt, nh)
+            grecs, gst = fb.scan_mem(text, True, True, 1, k, j, 100, b2, lt, nh)
+        finally:
+            fb.set_tuning("scan_memo", 1)
+        assert gst == ost and _strip(grecs) == _strip(orecs), memo
+
+
+def test_lower_case_bases_split_reads(fb, oracle, tmp_path_factory, impl):
+    """lower-case bases are not valid nucleotides (utils/Kmer.cpp:50-60): they split a read like an N does"""
+    _, text = _dataset(tmp_path_factory, "lower.fq", genome=40000, cov=25, length=120, insert=300, seed=41, err=0.005,
+                       nrate=0.004, lower=True)
+    assert any(c in text for c in (b"a", b"c", b"g", b"t"))
+    k, lt, nh = 27, 19, 3
+    o1, o2, ost = oracle.load_two_filters(text, True, k, lt, nh)
+    g2, g1, gst = fb.load_two_filters_mem(text, True, k, lt, nh, want_bloo1=True)
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    assert gst.kmers == ost.kmers and gst.unambiguous_reads == ost.unambiguous_reads
+    for no_cleaning in (1, 0):
+        sg, lg = oracle.geometry_optimal(2000, 0.01), oracle.geometry_optimal(4000, 0.01)
+        ospf, olpf = np.zeros((1 << sg[0]) // 8, np.uint8), np.zeros((1 << lg[0]) // 8, np.uint8)
+        gspf, glpf = ospf.copy(), olpf.copy()
+        orecs, osst = oracle.scan(text, True, True, no_cleaning, k, 1, 100, o2, lt, nh, ospf, sg, olpf, lg)
+        grecs, gsst = fb.scan_mem(text, True, True, no_cleaning, k, 1, 100, o2, lt, nh, gspf, sg, glpf, lg)
+        assert gsst == osst and _strip(grecs) == _strip(orecs)
+        assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
+
+
+def test_epochs_report_their_work(fb, oracle, tmp_path_factory):
+    """a deep-coverage stream spends most records in classify epochs; the exact set stays a small share of them"""
+    _, text = _dataset(tmp_path_factory, "deep_cov.fq", genome=60000, cov=120, length=150, insert=400, seed=51)
+    k = 31
+    lt, nh = _geom(oracle, 60000, 20000)
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    orecs, ost = oracle.scan(text, True, True, 1, k, 1, 100, b2, lt, nh)
+    try:
+        fb.set_tuning("epoch0", 1024)
+        grecs, gst = fb.scan_mem(text, True, True, 1, k, 1, 100, b2, lt, nh)
+        tim = fb.timings()
+    finally:
+        fb.set_tuning("epoch0", 8192)
+    assert gst == ost and _strip(grecs) == _strip(orecs)
+    assert tim["epochs_classify"] > 0 and tim["dry_records"] > ost["reads_processed"] // 2
+    assert tim["exact_records"] < ost["reads_processed"]
