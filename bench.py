@@ -277,7 +277,7 @@ def run_ours(args, w):
     barrier()
     clk = clocks.stop()
     launches = sess.launches - launches0
-    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry")}
+    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry", "stitch_verify", "stitch_flow_prep")}
     sess.set_profiling(False)
     lstats = sess.load_stats()
     stitch_info, n_junc = {}, 0

@@ -248,7 +248,7 @@ def scan(path, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, lo
 
 class Session:
     """device-resident stage API (faucet_session_* in include/faucet_gpu.h)"""
-    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4, "stitch_dry": 5}
+    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4, "stitch_dry": 5, "stitch_verify": 6, "stitch_flow_prep": 7}
 
     def __init__(self, k, log2_tai, n_hash, j=1, max_spacer_dist=100, max_text_bytes=1 << 30):
         self.h = C.c_void_p()

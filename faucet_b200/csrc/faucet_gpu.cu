@@ -20,6 +20,7 @@
 #include "scan.cuh"
 #include "pair_filter_host.hpp"
 #include "stitch.cuh"
+#include "flow.cuh"
 
 using namespace faucet;
 
@@ -42,6 +43,10 @@ struct Global {
   uint32_t epoch0 = 8192, epoch_max = 1u << 20;  // first / largest epoch, records
   uint32_t epoch_switch_pct = 30;                // an ordered epoch with fewer writers than this switches to classify epochs
   uint32_t epoch_shrink_pct = 14, epoch_grow_pct = 6;  // exact-set share above / below which the epoch halves / doubles
+  int stitch_exec = 1;                           // ordered executor: 1 = dataflow (flow.cuh), 0 = rounds with grid barriers (stitch.cuh)
+  uint32_t flow_chunk = 1u << 20;                // records per dependency sort of the dataflow executor
+  bool epoch_recheck = true;                     // records with earlier but no later writes under their slots are walked again on
+                                                 // the live table instead of joining the exact set
   int load_memo_log2 = 29;            // pass 1 caches saturated k-mers when the filter has at least 2^this bits
   int memo_shift = 1;                 // memo entries = Bloom bits >> memo_shift (8 bytes each): load <= ~0.3 of the 8-probe cache
   bool scan_memo = true;              // scan_flags looks the extension masks of a k-mer up before it computes them (scan.cuh)
@@ -66,7 +71,7 @@ int fail(int code, const std::string& msg) {
 
 constexpr size_t TAIL_MAX = (size_t)1 << 24;  // longest partial record carried between batches
 constexpr size_t TEXT_PAD = 2 * PARSE_CHUNK;
-enum { KT_PARSE = 0, KT_LOAD_A, KT_LOAD_B, KT_SCAN, KT_STITCH, KT_DRY, KT_COUNT };
+enum { KT_PARSE = 0, KT_LOAD_A, KT_LOAD_B, KT_SCAN, KT_STITCH, KT_DRY, KT_VERIFY, KT_FLOW_PREP, KT_COUNT };
 
 }  // namespace
 
@@ -112,7 +117,20 @@ struct faucet_session {
   uint32_t* d_recs = nullptr;   // REC_WORDS u32 per slot
   unsigned long long tbl_cap = 0;
   uint32_t* d_res = nullptr;
-  uint32_t* d_dirty = nullptr;  // epochs: smallest record that wrote a junction under each reservation slot
+  uint32_t* d_jslot = nullptr;  // one bit per reservation slot: a junction lives under it (stitch.cuh)
+  uint32_t *d_dirty = nullptr, *d_dirty_max = nullptr;  // epochs: first / last record that wrote a junction under each reservation slot
+  uint32_t* d_rows = nullptr;   // epochs: reservation slots of every record of the epoch (classify writes, verify reads)
+  size_t rows_cap = 0;
+  bool dry_ready = false;
+  // dataflow executor (flow.cuh)
+  uint32_t *d_frows = nullptr, *d_fpreds = nullptr, *d_fdone = nullptr, *d_fcounts = nullptr, *d_fcount_sums = nullptr;
+  size_t flow_cap = 0;
+  unsigned long long *d_fpairs = nullptr, *d_fpairs2 = nullptr;
+  uint32_t *d_fhist = nullptr, *d_fhist_sums = nullptr;
+  size_t fpairs_cap = 0, fhist_cap = 0;
+  unsigned int* d_fbig = nullptr;
+  const void* flow_fn = nullptr;
+  int flow_grid = 0;
   uint8_t* d_in_exact = nullptr;  // epochs: per record of the batch, member of the exact set
   size_t in_exact_cap = 0;
   uint32_t *d_list = nullptr, *d_eprefix = nullptr, *d_eprefix_sums = nullptr, *d_count = nullptr;  // the exact set as an ascending list
@@ -290,7 +308,7 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
     if (value < 64 || (value & (value - 1))) return fail(FAUCET_E_ARG, "table_cap0 must be a power of two >= 64");
     g.table_cap0 = value;
   } else if (n == "res_log2") {
-    if (value < 8 || value > 30) return fail(FAUCET_E_ARG, "res_log2 out of range");
+    if (value < 8 || value > 24) return fail(FAUCET_E_ARG, "res_log2 out of range (8..24)");
     g.res_log2 = (int)value;
   } else if (n == "stitch_w_max") {
     if (value < 1 || value > (1u << 22)) return fail(FAUCET_E_ARG, "stitch_w_max out of range");
@@ -304,6 +322,14 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "epoch_mode") {
     if (value > 2) return fail(FAUCET_E_ARG, "epoch_mode must be 0 (one ordered run), 1 (adaptive) or 2 (always classify)");
     g.epoch_mode = (int)value;
+  } else if (n == "stitch_exec") {
+    if (value > 1) return fail(FAUCET_E_ARG, "stitch_exec must be 0 (rounds) or 1 (dataflow)");
+    g.stitch_exec = (int)value;
+  } else if (n == "flow_chunk") {
+    if (value < 1 || value > (1u << 24)) return fail(FAUCET_E_ARG, "flow_chunk out of range");
+    g.flow_chunk = (uint32_t)value;
+  } else if (n == "epoch_recheck") {
+    g.epoch_recheck = value != 0;
   } else if (n == "epoch0" || n == "epoch_max") {
     if (value < 1 || value > (1u << 30)) return fail(FAUCET_E_ARG, "epoch size out of range");
     (n == "epoch0" ? g.epoch0 : g.epoch_max) = (uint32_t)value;
@@ -398,7 +424,9 @@ void faucet_session_destroy(faucet_session* s) {
   for (int i = 0; i < 3; i++) if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
   if (s->h_recs) cudaFreeHost(s->h_recs);
   cudaFree(s->d_bloom1); cudaFree(s->d_flags); cudaFree(s->d_seq_start); cudaFree(s->d_seq_end);
-  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res); cudaFree(s->d_dirty); cudaFree(s->d_in_exact);
+  cudaFree(s->d_st); cudaFree(s->d_keys); cudaFree(s->d_jstamps); cudaFree(s->d_recs); cudaFree(s->d_res); cudaFree(s->d_jslot); cudaFree(s->d_dirty); cudaFree(s->d_dirty_max); cudaFree(s->d_rows);
+  cudaFree(s->d_frows); cudaFree(s->d_fpreds); cudaFree(s->d_fdone); cudaFree(s->d_fcounts); cudaFree(s->d_fcount_sums);
+  cudaFree(s->d_fpairs); cudaFree(s->d_fpairs2); cudaFree(s->d_fhist); cudaFree(s->d_fhist_sums); cudaFree(s->d_fbig); cudaFree(s->d_in_exact);
   cudaFree(s->d_list); cudaFree(s->d_eprefix); cudaFree(s->d_eprefix_sums); cudaFree(s->d_count); cudaFree(s->d_snap_keys); cudaFree(s->d_snap_recs);
   cudaFree(s->d_st_snap); cudaFree(s->d_spf_snap);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
@@ -773,6 +801,8 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
     if ((rc = dmalloc(&s->d_res, (size_t)1 << g.res_log2))) return rc;
     CU(cudaMemsetAsync(s->d_res, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
   }
+  if (!s->d_jslot && (rc = dmalloc(&s->d_jslot, ((size_t)1 << g.res_log2) / 32 + 1))) return rc;
+  CU(cudaMemsetAsync(s->d_jslot, 0, (((size_t)1 << g.res_log2) / 32 + 1) * 4, s->stream));
   if (s->w_max > s->deferred_cap) {
     for (int i = 0; i < 2; i++) {
       cudaFree(s->d_deferred[i]); s->d_deferred[i] = nullptr;
@@ -784,6 +814,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
   unsigned int w0 = std::min(g.stitch_w0, s->w_max);
   CU(cudaMemcpyAsync(&s->d_st->W, &w0, 4, cudaMemcpyHostToDevice, s->stream));
   s->h_st = StitchState();
+  s->h_st.W = w0;
   // short pair filter: adds only (src/ReadScanner.cpp:208-225) => atomicOr on a device copy
   cudaFree(s->d_spf); s->d_spf = nullptr; s->h_spf = nullptr;
   cudaFree(s->d_spf_snap); s->d_spf_snap = nullptr;
@@ -822,7 +853,7 @@ static void stitch_fill_args(faucet_session* s, StitchArgs& a) {
   a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
   a.res = s->d_res; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
   a.deferred[0] = s->d_deferred[0]; a.deferred[1] = s->d_deferred[1];
-  a.st = s->d_st; a.special = &s->d_st->special;
+  a.st = s->d_st; a.special = &s->d_st->special; a.jslot = s->d_jslot;
   a.spf = s->d_spf; a.spf_mask = s->d_spf ? ((1ull << s->spf_log2) - 1) : 0; a.spf_nh = s->spf_nh;
   a.ext = s->lpf.enabled() ? s->d_ext : nullptr; a.ext_cap = s->ext_cap;
   a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
@@ -855,7 +886,7 @@ static int stitch_run_ordered(faucet_session* s, const uint32_t* list, uint32_t 
     StitchArgs a;
     stitch_fill_args(s, a);
     a.n_recs = end; a.list = list;
-    a.dirty = mark_dirty ? s->d_dirty : nullptr;
+    a.dirty = mark_dirty ? s->d_dirty : nullptr; a.dirty_max = mark_dirty ? s->d_dirty_max : nullptr;
     void* params[] = {&a};
     {
       KTimer kt(s, KT_STITCH);
@@ -889,6 +920,147 @@ static int stitch_run_ordered(faucet_session* s, const uint32_t* list, uint32_t 
   return 0;
 }
 
+// in-place exclusive prefix sum of n u32 (stitch.cuh's scan kernels); sums = scratch of n / SCAN_CHUNK + 2 entries
+static void exclusive_scan_u32(faucet_session* s, uint32_t* data, unsigned long long n, uint32_t* sums) {
+  const unsigned long long nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  scan_reduce_kernel<<<(unsigned)nb, 256, 0, s->stream>>>(data, n, sums);
+  scan_sums_kernel<<<1, 1024, 0, s->stream>>>(sums, nb);
+  scan_apply_kernel<<<(unsigned)nb, 256, 0, s->stream>>>(data, n, sums);
+  s->launches += 3;
+}
+
+static int stitch_run_ordered(faucet_session* s, const uint32_t* list, uint32_t begin, uint32_t end, bool mark_dirty,
+                              bool allow_grow, bool* need_grow);
+
+// The ordered execution of the entries [begin, end) of `list` (NULL: the records themselves) by the dataflow
+// executor (flow.cuh): dependency sort, then one persistent kernel, in chunks of g.flow_chunk records.  Same
+// contract as stitch_run_ordered, which still takes the lists that hold a line with more slots than a row.
+static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t begin, uint32_t end, bool mark_dirty,
+                           bool allow_grow, bool* need_grow) {
+  if (need_grow) *need_grow = false;
+  if (g.stitch_exec == 0) return stitch_run_ordered(s, list, begin, end, mark_dirty, allow_grow, need_grow);
+  int rc;
+  if (!s->flow_fn) {
+    int per_sm = 0;
+    const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
+    s->flow_fn = (const void*)stitch_flow_kernel<FAUCET_FLOW_BLOCKS>;
+    CU(cudaFuncSetAttribute(s->flow_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->flow_fn, STITCH_THREADS, smem));
+    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_flow_kernel cannot be made resident");
+    s->flow_grid = per_sm * g.sm_count;
+    if ((rc = dmalloc(&s->d_fbig, 1))) return rc;
+  }
+  const int grid = g.sm_count * 8;
+  for (uint32_t b0 = begin; b0 < end;) {
+    const uint32_t n = std::min<uint32_t>(end - b0, g.flow_chunk);
+    if (n > s->flow_cap) {
+      cudaFree(s->d_frows); cudaFree(s->d_fpreds); cudaFree(s->d_fdone); cudaFree(s->d_fcounts); cudaFree(s->d_fcount_sums);
+      s->d_frows = s->d_fpreds = s->d_fdone = s->d_fcounts = s->d_fcount_sums = nullptr;
+      s->flow_cap = (size_t)n + n / 4 + 1024;
+      if ((rc = dmalloc(&s->d_frows, s->flow_cap * ROW_WORDS)) || (rc = dmalloc(&s->d_fpreds, s->flow_cap * ROW_WORDS)) ||
+          (rc = dmalloc(&s->d_fdone, s->flow_cap)) || (rc = dmalloc(&s->d_fcounts, s->flow_cap + 1)) ||
+          (rc = dmalloc(&s->d_fcount_sums, s->flow_cap / SCAN_CHUNK + 4)))
+        return rc;
+    }
+    StitchArgs a;
+    stitch_fill_args(s, a);
+    a.list = list ? list + b0 : nullptr;
+    a.n_recs = n;
+    a.dirty = mark_dirty ? s->d_dirty : nullptr; a.dirty_max = mark_dirty ? s->d_dirty_max : nullptr;
+    FlowArgs f;
+    std::memset(&f, 0, sizeof f);
+    f.n = n; f.begin = b0; f.rows = s->d_frows; f.preds = s->d_fpreds; f.done = s->d_fdone; f.counts = s->d_fcounts; f.big = s->d_fbig;
+    uint32_t tail[2] = {0, 0};  // last count and its prefix: their sum is the number of pairs
+    unsigned int big = 0;
+    {
+      KTimer kt(s, KT_FLOW_PREP);
+      CU(cudaMemsetAsync(s->d_fbig, 0, 4, s->stream));
+      flow_rows_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(a, f);
+      CU(cudaMemcpyAsync(&tail[0], s->d_fcounts + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+      exclusive_scan_u32(s, s->d_fcounts, n, s->d_fcount_sums);
+      CU(cudaMemcpyAsync(&tail[1], s->d_fcounts + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+      CU(cudaMemcpyAsync(&big, s->d_fbig, 4, cudaMemcpyDeviceToHost, s->stream));
+      s->launches++;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    if ((rc = check_launch("flow_rows"))) return rc;
+    if (big) {  // a line with more slots than a row holds: this chunk goes through the rounds
+      if ((rc = stitch_run_ordered(s, list, b0, b0 + n, mark_dirty, allow_grow, need_grow))) return rc;
+      if (need_grow && *need_grow) return 0;
+      b0 += n;
+      continue;
+    }
+    const uint32_t n_pairs = tail[0] + tail[1];
+    f.n_pairs = n_pairs;
+    f.n_sub = (n_pairs + RADIX_SUB - 1) / RADIX_SUB;
+    if (n_pairs > s->fpairs_cap) {
+      cudaFree(s->d_fpairs); cudaFree(s->d_fpairs2); s->d_fpairs = s->d_fpairs2 = nullptr;
+      s->fpairs_cap = (size_t)n_pairs + n_pairs / 4 + 1024;
+      if ((rc = dmalloc(&s->d_fpairs, s->fpairs_cap)) || (rc = dmalloc(&s->d_fpairs2, s->fpairs_cap))) return rc;
+    }
+    if ((size_t)f.n_sub * 256 > s->fhist_cap) {
+      cudaFree(s->d_fhist); cudaFree(s->d_fhist_sums); s->d_fhist = s->d_fhist_sums = nullptr;
+      s->fhist_cap = (size_t)f.n_sub * 256 + 1024;
+      if ((rc = dmalloc(&s->d_fhist, s->fhist_cap)) || (rc = dmalloc(&s->d_fhist_sums, s->fhist_cap / SCAN_CHUNK + 4))) return rc;
+    }
+    f.pairs = s->d_fpairs; f.pairs2 = s->d_fpairs2; f.hist = s->d_fhist;
+    {
+      KTimer kt(s, KT_FLOW_PREP);
+      flow_pairs_kernel<<<grid, 256, 0, s->stream>>>(f);
+      s->launches++;
+      if (n_pairs) {
+        const unsigned rgrid = (f.n_sub + RADIX_THREADS / 32 - 1) / (RADIX_THREADS / 32);
+        for (int shift = 0; shift < g.res_log2; shift += 8) {  // stable LSD passes over the slot
+          f.shift = shift;
+          radix_hist_kernel<<<rgrid, RADIX_THREADS, 0, s->stream>>>(f);
+          exclusive_scan_u32(s, s->d_fhist, (unsigned long long)f.n_sub * 256, s->d_fhist_sums);
+          radix_scatter_kernel<<<rgrid, RADIX_THREADS, 0, s->stream>>>(f);
+          std::swap(f.pairs, f.pairs2);
+          s->launches += 2;
+        }
+        flow_preds_kernel<<<grid, 256, 0, s->stream>>>(f);
+        s->launches++;
+      }
+      CU(cudaMemsetAsync(s->d_fdone, 0, (size_t)n * 4, s->stream));
+    }
+    // ---- run; relaunched after the table grew / the extension lists were drained
+    while (true) {
+      struct { unsigned int next, nd[2], W, round, status; } z = {0, {0, 0}, s->h_st.W, s->h_st.round, ST_DONE};
+      CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
+      void* params[] = {&a, &f};
+      {
+        KTimer kt(s, KT_STITCH);
+        CU(cudaLaunchCooperativeKernel(s->flow_fn, dim3(s->flow_grid), dim3(STITCH_THREADS), params,
+                                       STITCH_WARPS * sizeof(WarpScratch), s->stream));
+        s->launches++;
+      }
+      CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
+      CU(cudaStreamSynchronize(s->stream));
+      if ((rc = check_launch("stitch_flow"))) return rc;
+      const unsigned int status = s->h_st.status;
+      if (status == ST_DONE) break;
+      if (status == ST_GROW_TABLE) {
+        if (!allow_grow) { *need_grow = true; return 0; }
+        if ((rc = stitch_grow_table(s))) return rc;
+        a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
+      } else if (status == ST_DRAIN_EXT) {
+        if (s->h_st.ext_used == 0) {
+          cudaFree(s->d_ext); s->d_ext = nullptr;
+          s->ext_cap *= 2;
+          if ((rc = dmalloc(&s->d_ext, s->ext_cap))) return rc;
+          a.ext = s->d_ext; a.ext_cap = s->ext_cap;
+        } else if ((rc = stitch_drain_ext(s))) {
+          return rc;
+        }
+      } else {
+        return fail(FAUCET_E_CUDA, "stitch flow kernel returned an unknown status");
+      }
+    }
+    b0 += n;
+  }
+  return 0;
+}
+
 static int stitch_ensure_epoch_buffers(faucet_session* s, uint32_t m) {
   int rc;
   if (s->n_recs > s->in_exact_cap) {
@@ -904,7 +1076,16 @@ static int stitch_ensure_epoch_buffers(faucet_session* s, uint32_t m) {
         (rc = dmalloc(&s->d_eprefix_sums, s->list_cap / SCAN_CHUNK + 2)))
       return rc;
   }
-  if (!s->d_dirty && (rc = dmalloc(&s->d_dirty, (size_t)1 << g.res_log2))) return rc;
+  if (!s->d_dirty && ((rc = dmalloc(&s->d_dirty, (size_t)1 << g.res_log2)) || (rc = dmalloc(&s->d_dirty_max, (size_t)1 << g.res_log2)))) return rc;
+  if ((size_t)m > s->rows_cap) {
+    cudaFree(s->d_rows); s->d_rows = nullptr;
+    s->rows_cap = (size_t)m + m / 4 + 1024;
+    if ((rc = dmalloc(&s->d_rows, s->rows_cap * ROW_WORDS))) return rc;
+  }
+  if (!s->dry_ready) {
+    CU(cudaFuncSetAttribute((const void*)stitch_dry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DRY_WARPS * sizeof(DryScratch))));
+    s->dry_ready = true;
+  }
   if (s->snap_cap != s->tbl_cap) {
     cudaFree(s->d_snap_keys); cudaFree(s->d_snap_recs);
     s->d_snap_keys = nullptr; s->d_snap_recs = nullptr; s->snap_cap = 0;
@@ -935,29 +1116,38 @@ static int stitch_restore(faucet_session* s, size_t h_ext_mark) {
 static int stitch_epoch_classify(faucet_session* s, uint32_t r, uint32_t m, uint32_t* n_exact_out) {
   int rc;
   // headroom the ordered kernel itself would ask for, before the snapshot pins the slots
-  while (s->h_st.n_entries + s->h_st.max_need * s->w_max > s->tbl_cap / 2)
+  while (s->h_st.n_entries + s->h_st.max_need * (g.stitch_exec ? (unsigned long long)s->stitch_grid * STITCH_WARPS : s->w_max) > s->tbl_cap / 2)
     if ((rc = stitch_grow_table(s))) return rc;
   if ((rc = stitch_ensure_epoch_buffers(s, m))) return rc;
   const int grid = g.sm_count * 8;
+  const size_t dry_smem = DRY_WARPS * sizeof(DryScratch);
   StitchArgs d;
   stitch_fill_args(s, d);
-  d.keys = s->d_snap_keys; d.recs = s->d_snap_recs; d.special = &s->d_st_snap->special;
-  d.cov_out = s->d_recs; d.in_exact = s->d_in_exact; d.r_begin = r; d.r_end = r + m; d.dirty = s->d_dirty;
-  if ((rc = stitch_snapshot(s))) return rc;
-  CU(cudaMemsetAsync(s->d_in_exact + r, 0, m, s->stream));
-  {
+  // classify walks the live table, which is T0 until the exact set runs; with no pair filter to feed, the quiet
+  // records commit their coverage counts right away
+  const bool fused = !d.spf && !d.ext;
+  d.in_exact = s->d_in_exact; d.r_begin = r; d.r_end = r + m; d.dirty = s->d_dirty; d.dirty_max = s->d_dirty_max;
+  d.rows = s->d_rows; d.rows_base = r; d.recheck = g.epoch_recheck ? 1 : 0;
+  d.taint_mark = fused ? EX_COMMITTED : EX_MEMBER;
+  // a walk of the records flagged `want`, on the live table or on the snapshot
+  auto dry = [&](int mode, uint8_t want, uint8_t after, bool live, uint32_t x0, uint32_t x1) {
+    StitchArgs w = d;
+    w.dry_mode = mode; w.want_flag = want; w.flag_after = after; w.r_begin = x0; w.r_end = x1;
+    if (!live) { w.keys = s->d_snap_keys; w.recs = s->d_snap_recs; w.special = &s->d_st_snap->special; }
+    w.cov_out = s->d_recs;
     KTimer kt(s, KT_DRY);
-    d.dry_mode = DRY_CLASSIFY;
-    stitch_dry_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
+    stitch_dry_kernel<<<grid, DRY_THREADS, dry_smem, s->stream>>>(w);
     s->launches++;
-  }
-  CU(cudaMemcpyAsync(s->d_st_snap, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToDevice, s->stream));  // keeps classify's counters
+  };
+  CU(cudaMemsetAsync(s->d_in_exact + r, 0, m, s->stream));
+  dry(fused ? DRY_CLASSIFY_APPLY : DRY_CLASSIFY, 0, 0, true, r, r + m);
+  if ((rc = stitch_snapshot(s))) return rc;  // T0 (+ the counts the quiet records just added)
   const size_t h_ext_mark = s->h_ext.size();
   const unsigned n_blocks = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
   uint32_t n_exact = 0, n_prev = 0;
   for (int iter = 0;; iter++) {
     {
-      KTimer kt(s, KT_DRY);
+      KTimer kt(s, KT_VERIFY);
       exact_flags_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix);
       scan_reduce_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
       scan_sums_kernel<<<1, 1024, 0, s->stream>>>(s->d_eprefix_sums, n_blocks);
@@ -972,40 +1162,60 @@ static int stitch_epoch_classify(faucet_session* s, uint32_t r, uint32_t m, uint
     if (n_exact == 0 || (iter > 0 && n_exact == n_prev)) break;  // nothing (more) joined: the live table is final
     if (iter > 0 && (rc = stitch_restore(s, h_ext_mark))) return rc;
     CU(cudaMemsetAsync(s->d_dirty, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+    CU(cudaMemsetAsync(s->d_dirty_max, 0, ((size_t)1 << g.res_log2) * 4, s->stream));
     bool need_grow = false;
-    if ((rc = stitch_run_ordered(s, s->d_list, 0, n_exact, true, false, &need_grow))) return rc;
+    if ((rc = stitch_run_flow(s, s->d_list, 0, n_exact, true, false, &need_grow))) return rc;
     s->ep.exact_runs += n_exact;
     s->ep.iterations++;
     if (need_grow) {  // the slots of T0 are about to move: undo the epoch, grow, and take it in order instead
-      if ((rc = stitch_restore(s, h_ext_mark)) || (rc = stitch_grow_table(s))) return rc;
+      if ((rc = stitch_restore(s, h_ext_mark))) return rc;
+      if (fused) {  // every record that committed under T0 takes it back
+        exact_mark_applied_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m);
+        s->launches++;
+        dry(DRY_RETRACT, EX_COMMITTED, EX_RETRACTED, false, r, r + m);
+      }
+      if ((rc = stitch_grow_table(s))) return rc;
       s->ep.fallbacks++;
       *n_exact_out = m;
-      return stitch_run_ordered(s, nullptr, r, r + m, false, true, nullptr);
+      return stitch_run_flow(s, nullptr, r, r + m, false, true, nullptr);
     }
     {
-      KTimer kt(s, KT_DRY);
+      KTimer kt(s, KT_VERIFY);
       stitch_verify_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
+      s->launches++;
+    }
+    if (d.recheck) dry(DRY_RECHECK, EX_RECHECK, 0, true, r, r + m);
+    if (fused) {  // what joined had committed under T0: take that back, from the live table and from the snapshot
+      StitchArgs w = d;
+      w.dry_mode = DRY_RETRACT; w.want_flag = EX_COMMITTED; w.flag_after = EX_RETRACTED;
+      w.keys = s->d_snap_keys; w.recs = s->d_snap_recs; w.special = &s->d_st_snap->special;
+      w.cov_out = s->d_recs; w.cov_out2 = s->d_snap_recs; w.st2 = s->d_st_snap;
+      KTimer kt(s, KT_DRY);
+      stitch_dry_kernel<<<grid, DRY_THREADS, dry_smem, s->stream>>>(w);
       s->launches++;
     }
     n_prev = n_exact;
   }
-  // apply: the records outside the exact set, against T0
-  d.st = s->d_st;
-  d.dry_mode = DRY_APPLY;
-  if (!d.ext) {
-    KTimer kt(s, KT_DRY);
-    stitch_dry_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
-    s->launches++;
-  } else {  // bounded launches: a quiet record emits at most LAND_CAP extensions plus chunk headers
-    const uint32_t per_rec = LAND_CAP + LAND_CAP / (EXT_STAGE - 1) + 2;
-    for (uint32_t x = r; x < r + m;) {
-      if ((rc = stitch_drain_ext(s))) return rc;
-      const uint32_t fit = (uint32_t)std::max<unsigned long long>(1, s->ext_cap / per_rec);
-      d.r_begin = x; d.r_end = (uint32_t)std::min<uint64_t>((uint64_t)x + fit, (uint64_t)r + m);
-      KTimer kt(s, KT_DRY);
-      stitch_dry_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(d);
-      s->launches++;
-      x = d.r_end;
+  // commit what has not committed yet.  EX_QUIET records saw T0; EX_SETTLED records saw the live table.
+  if (fused) {
+    if (n_exact) {  // (no exact set: nothing was written, nobody is settled)
+      dry(DRY_RETRACT, EX_SETTLED, EX_SETTLED, false, r, r + m);
+      dry(DRY_APPLY, EX_SETTLED, 0, true, r, r + m);
+    }
+  } else {
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1 && !n_exact) break;
+      const uint8_t want = pass ? EX_SETTLED : EX_QUIET;
+      if (!d.ext) { dry(DRY_APPLY, want, 0, pass == 1, r, r + m); continue; }
+      // bounded launches: a quiet record emits at most LAND_CAP extensions plus chunk headers
+      const uint32_t per_rec = LAND_CAP + LAND_CAP / (EXT_STAGE - 1) + 2;
+      for (uint32_t x = r; x < r + m;) {
+        if ((rc = stitch_drain_ext(s))) return rc;
+        const uint32_t fit = (uint32_t)std::max<unsigned long long>(1, s->ext_cap / per_rec);
+        const uint32_t x1 = (uint32_t)std::min<uint64_t>((uint64_t)x + fit, (uint64_t)r + m);
+        dry(DRY_APPLY, want, 0, pass == 1, x, x1);
+        x = x1;
+      }
     }
   }
   CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
@@ -1028,7 +1238,7 @@ int faucet_session_stitch_batch(faucet_session* s) {
     const bool classify = g.epoch_mode == 2 || (g.epoch_mode == 1 && !s->ep_exact);
     if (!classify) {
       const unsigned long long w0 = s->h_st.stats[SS_WRITERS];
-      if ((rc = stitch_run_ordered(s, nullptr, r, r + m, false, true, nullptr))) return rc;
+      if ((rc = stitch_run_flow(s, nullptr, r, r + m, false, true, nullptr))) return rc;
       const unsigned long long writers = s->h_st.stats[SS_WRITERS] - w0;
       s->ep.exact_epochs++; s->ep.exact_runs += m;
       s->ep_size = (uint32_t)std::min<uint64_t>((uint64_t)s->ep_size * 2, g.epoch_max);

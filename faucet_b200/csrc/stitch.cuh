@@ -41,7 +41,9 @@
 //   verify    a record outside E whose line touches a slot written by an EARLIER record may have seen a
 //             stale T0: it joins E, the table is restored to T0 and E runs again -- until nothing joins;
 //   apply     the records outside E (quiet under T0, and T0 is what they would have seen) add their
-//             coverage counts, again fully parallel, reading T0 (stitch_dry_kernel).
+//             coverage counts, again fully parallel, reading T0 (stitch_dry_kernel).  When the scan has no
+//             pair filters to feed, classify applies at once and the few records that verify adds to E are
+//             retracted (the same walk, counts subtracted) before E runs again.
 // By induction over the stream every record outside E behaves exactly as in the sequential run (its keys are
 // untouched before its turn), so E -- executed in order from T0 -- sees exactly the sequential state.
 //
@@ -69,7 +71,11 @@ constexpr int STITCH_WARPS = STITCH_THREADS / 32;
 constexpr unsigned long long KEY_EMPTY = ~0ull;
 constexpr uint32_t RES_FREE = 0xffffffffu;
 constexpr int EXT_STAGE = 32;   // staged real-extension k-mers per warp before a chunk is flushed
-constexpr int POS_CAP = 256;    // k-mer positions per line served from shared memory (longer lines: direct path)
+#ifndef FAUCET_POS_CAP
+#define FAUCET_POS_CAP 256
+#endif
+constexpr int POS_CAP = FAUCET_POS_CAP;  // k-mer positions per line served from shared memory (longer lines: direct path)
+constexpr int PK_WORDS = (15 + POS_CAP + 32 + 15) / 16 + 1, INV_WORDS = (31 + POS_CAP + 32 + 31) / 32 + 1;  // plane words of such a line
 constexpr int RES_CAP = 96;     // reservation slots per line kept in shared memory
 constexpr int VIS_CAP = 32;     // junction slots a line touched (beyond it every skip distance is re-read)
 constexpr int REC_WORDS = 16;   // u32 per junction record
@@ -79,7 +85,17 @@ constexpr unsigned long long STAMP_LOW = (1ull << STAMP_SHIFT) - 1ull;
 constexpr int LAND_CAP = 160;   // junctions one line may land on in the read-only walk (more: the ordered kernel takes it)
 constexpr int DRY_THREADS = 256;
 constexpr int DRY_WARPS = DRY_THREADS / 32;
-enum { DRY_CLASSIFY = 0, DRY_APPLY = 1 };
+enum { DRY_CLASSIFY = 0, DRY_APPLY = 1, DRY_CLASSIFY_APPLY = 2, DRY_RETRACT = 3, DRY_RECHECK = 4 };
+// in_exact[] of a classify epoch.  Members of the exact set: EX_*.
+enum { EX_QUIET = 0,      // quiet under T0 and no earlier write under its slots: T0 is what it would have seen
+       EX_MEMBER = 1,     // exact set; never committed
+       EX_COMMITTED = 2,  // exact set; had committed under T0 at classify time: to be retracted
+       EX_RETRACTED = 3,  // exact set; retracted
+       EX_SETTLED = 4,    // earlier writes under its slots but none later, and quiet on the LIVE table (= the state it would have seen)
+       EX_RECHECK = 5 };  // earlier writes, none later: to be walked on the live table
+constexpr uint32_t ROW_SLOT_MASK = 0xffffffu;  // a listed reservation slot = slot | first position of its run << 24 (res_log2 <= 24)
+constexpr int ROW_WORDS = 32;   // reservation row of a record: [0] = count (255: recompute), [1..31] = slots
+
 
 enum { ST_DONE = 0, ST_GROW_TABLE = 1, ST_DRAIN_EXT = 2, ST_MORE_ROWS = 3, ST_STUCK = 4 };
 enum { SS_JCHECK = 0, SS_NOJUNC, SS_PROCESSED, SS_SKIPPED, SS_NOERR, SS_UNAMBIG, SS_ROUNDS, SS_DEFERRED,
@@ -121,11 +137,22 @@ struct StitchArgs {
   unsigned long long cap;        // power of two, < 2^31
   uint32_t* res;                 // reservation table
   uint32_t res_mask;
+  uint32_t* jslot;               // one bit per reservation slot: some junction's k-mer has that minimizer (never cleared during
+                                 // a scan, so it may err towards set): runs of a line with a clear bit need no table lookup
   uint32_t* dirty;               // same slots: smallest record index that wrote a junction whose k-mer has that minimizer
-                                 // (ordered kernel marks, verify reads; NULL outside classify epochs)
+                                 // (ordered kernel marks, verify reads; NULL outside classify epochs) ...
+  uint32_t* dirty_max;           // ... and 1 + the largest such index
   // read-only walk (stitch_dry_kernel / stitch_verify_kernel): keys/recs above are the epoch's T0 snapshot
   uint32_t* cov_out;             // records of the LIVE table: apply adds the coverage counts here (same slots as T0)
-  uint8_t* in_exact;             // per record of the batch: 1 = member of the exact set
+  uint32_t* cov_out2;            // retract: the snapshot's records too (a later restore must not bring the counts back)
+  StitchState* st2;              // retract: the snapshot's counters too
+  uint8_t* in_exact;             // per record of the batch: 0 = quiet (applied, if classify applies), 1 = exact set (never
+                                 // applied), 2 = joined the exact set after it was applied, 3 = the same, retracted
+  uint8_t taint_mark;            // what joins the exact set after classify gets: EX_MEMBER, or EX_COMMITTED when classify applied
+  uint8_t want_flag, flag_after; // apply / retract / recheck take the records with in_exact == want_flag; retract leaves flag_after
+  uint8_t recheck;               // verify: records with earlier but no later writes are rechecked on the live table (else they join)
+  uint32_t* rows;                // classify writes, verify and the later walks read: ROW_WORDS u32 per record of the epoch
+  uint32_t rows_base;            // record of row 0
   uint32_t r_begin, r_end;       // the epoch
   int dry_mode;
   uint32_t* deferred[2];         // w_max entries each
@@ -141,12 +168,15 @@ struct StitchArgs {
 };
 
 struct WarpScratch {             // shared memory of one warp; filled in phase 1, consumed in phase 2
-  unsigned long long kmer[POS_CAP];   // forward k-mer of every position of the line
   int slot[2 * POS_CAP];              // table slot of the key at half-step 2*pos+dir, -1 = not a junction
-  uint8_t hop[2 * POS_CAP];           // stored dist[fwdIdx] of that junction when the round started
+  uint8_t hop[2 * POS_CAP];           // stored dist[fwdIdx] of that junction when the round started ...
+  uint8_t dback[2 * POS_CAP];         // ... its dist[backIdx] ...
+  uint8_t lnk[2 * POS_CAP];           // ... and its link mask (the read-only walk checks them instead of writing)
   uint8_t flag[POS_CAP];              // scan_flags byte of the position
-  uint32_t pk[24];                    // the line's words of the 2-bit plane, from word ls>>4
-  uint32_t inv[12];                   // the line's words of the validity plane, from word ls>>5
+  uint8_t plist[POS_CAP];             // the positions whose keys have to be looked up (prefetch_line)
+  uint32_t pmask[POS_CAP / 32];       // the same as a bit mask
+  uint32_t pk[PK_WORDS];              // the line's words of the 2-bit plane, from word ls>>4
+  uint32_t inv[INV_WORDS];            // the line's words of the validity plane, from word ls>>5
   uint32_t reskey[RES_CAP];           // reservation slots of the line
   int visited[VIS_CAP];               // slots of the junctions this line has touched
   unsigned long long stage[EXT_STAGE];
@@ -259,7 +289,7 @@ __device__ bool line_reservations(const StitchArgs& a, const uint32_t* packed, u
       if (MODE == 0 && active) atomicMin(slot, rec);
       const uint32_t b = __ballot_sync(0xffffffffu, active);
       const int at = nkeep + __popc(b & ((1u << lane) - 1u));
-      if (active && at < keep_cap) keep[at] = m & a.res_mask;
+      if (active && at < keep_cap) keep[at] = (m & a.res_mask) | ((base + lane < 255u ? base + lane : 255u) << 24);
       nkeep += __popc(b);
     }
     if (MODE == 1 && active && __ldcg(slot) != rec) ok = false;
@@ -406,6 +436,10 @@ __device__ __forceinline__ void out_finish(const StitchArgs& a, const OutList& o
   }
 }
 
+// forward k-mer at position `pos` of the line staged in c.S
+__device__ __forceinline__ uint64_t line_kmer(const StitchArgs& a, const WarpCtx& c, int pos) {
+  return kmer_at_t<true>(c.S->pk, (c.ls & 15u) + pos, a.k);
+}
 // has this line already touched `slot`?  (then the skip distance parked in phase 1 may be stale)
 __device__ __forceinline__ bool line_visited(const WarpCtx& c, int slot, int lane) {
   if (c.n_vis > VIS_CAP) return true;
@@ -420,16 +454,21 @@ __device__ __forceinline__ void line_visit(WarpCtx& c, int slot, int lane) {
 // a key this line just created: every other half-step of the line with that key must now see it
 __device__ __forceinline__ void line_publish(const StitchArgs& a, WarpCtx& c, uint64_t key, int slot, int lane) {
   for (int pos = lane; pos < c.n_pos; pos += 32) {
-    const uint64_t f = c.S->kmer[pos];
+    const uint64_t f = line_kmer(a, c, pos);
     if (f == key) c.S->slot[2 * pos + 1] = slot;
     if (revcomp(f, a.k) == key) c.S->slot[2 * pos] = slot;
   }
   __syncwarp();
 }
 // epoch bookkeeping of the ordered kernel: a junction with this key was created or had a distance raised by `rec`
-__device__ __forceinline__ void mark_dirty(const StitchArgs& a, uint64_t key, uint32_t rec, int lane) {
+// (and `created`: the slot now holds a junction)
+__device__ __forceinline__ void mark_written(const StitchArgs& a, uint64_t key, uint32_t rec, bool created, bool visible, int lane) {
+  if (!created && !(visible && a.dirty)) return;
   const uint32_t slot = kmer_res_slot(key, a.k, a.res_mask, lane);
-  if (lane == 0) atomicMin(a.dirty + slot, rec);
+  if (lane == 0) {
+    if (created) atomicOr(a.jslot + (slot >> 5), 1u << (slot & 31u));
+    if (visible && a.dirty) { atomicMin(a.dirty + slot, rec); atomicMax(a.dirty_max + slot, rec + 1u); }
+  }
 }
 
 // one lane: the junction updates of a landing.  Returns bit 0: this junction changed visibly (created / distance
@@ -517,7 +556,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
     if (!found) break;
     // ---- the junction at half-step tp (:134-192)
     const int pos = tp >> 1, dir = tp & 1;
-    const uint64_t fwd = FAST ? c.S->kmer[rel + pos] : kmer_at_t<false>(a.packed, s0 + pos, k);
+    const uint64_t fwd = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
     const uint64_t key = dir ? fwd : revcomp(fwd, k);
     const int real = dir ? (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base)
                          : (int)nt_comp(code_at_t<FAST>(c.pk, s0 + pos - 1 - c.pk_base));
@@ -550,10 +589,8 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
     wr = __shfl_sync(0xffffffffu, wr, 0);
     if (wr) {
       c.wrote = true;
-      if (a.dirty) {
-        if (wr & 1u) mark_dirty(a, key, c.rec, lane);
-        if (wr & 2u) mark_dirty(a, last_key, c.rec, lane);
-      }
+      mark_written(a, key, c.rec, created, (wr & 1u) != 0, lane);
+      mark_written(a, last_key, c.rec, false, (wr & 2u) != 0, lane);
     }
     out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
     have_last = true;
@@ -562,7 +599,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
   }
   if (!have_last) {  // add_fake_junction (:92-104): mid-read, facing forward
     const int pos = len / 2 - k / 2;
-    const uint64_t key = FAST ? c.S->kmer[rel + pos] : kmer_at_t<false>(a.packed, s0 + pos, k);
+    const uint64_t key = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
     const int real = (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base);
     int slot = 0;
     bool created = false;
@@ -581,7 +618,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
     created = __shfl_sync(0xffffffffu, (int)created, 0) != 0;
     c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
     wr = __shfl_sync(0xffffffffu, wr, 0);
-    if (wr) { c.wrote = true; if (a.dirty) mark_dirty(a, key, c.rec, lane); }
+    if (wr) { c.wrote = true; mark_written(a, key, c.rec, created, true, lane); }
     if (FAST && created) line_publish(a, c, key, slot, lane);
     line_visit(c, slot, lane);
     out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
@@ -592,19 +629,22 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       wr = atomicMax(rec_field(a, last_slot, REC_DIST + last_fwd_idx), dv) < dv;
     }
     wr = __shfl_sync(0xffffffffu, wr, 0);
-    if (wr) { c.wrote = true; if (a.dirty) mark_dirty(a, last_key, c.rec, lane); }
+    if (wr) { c.wrote = true; mark_written(a, last_key, c.rec, false, true, lane); }
   }
   __syncwarp();
   out_finish(a, o, pairs, lane);
 }
 
-// The same walk READ-ONLY against the epoch's snapshot (a.keys / a.recs): returns false as soon as the sub-read
-// would create a junction, raise a stored distance or set a new link (then the record belongs to the ordered
-// kernel).  A quiet sub-read leaves its landings in c.land_* (coverage counts, added when the record commits),
-// its counters in c.cnt and, when c.emit, its pair-filter / extension-list side effects.
+// The same walk READ-ONLY against the table in a.keys / a.recs: returns false as soon as the sub-read would create a
+// junction, raise a stored distance or set a new link (then the record belongs to the ordered kernel).  A quiet
+// sub-read leaves its landings in c.land_* (coverage counts, added when the record commits), its counters in c.cnt
+// and, when c.emit, its pair-filter / extension-list side effects.
+// FAST: slots, distances and link masks of every half-step of the line were parked in c.S by prefetch_line.
+template <bool FAST>
 __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int len, int lane) {
   const int k = a.k, j = a.j;
   const uint64_t mask = kmer_mask(k);
+  const int rel = (int)(s0 - c.ls);
   const int tested_end = 2 * len - 2 * k + 1 - 2 * j;
   int tp = 2 * j + 1, last_junc_pos = 0;
   bool have_last = false;
@@ -621,7 +661,7 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
     return true;
   };
   // dist[0..4] and the link mask of a junction, one word per lane 0..5 (one 32-byte sector of the record)
-  auto head = [&](int slot) -> uint32_t { return lane < 6 ? __ldg(a.recs + (size_t)slot * REC_WORDS + lane) : 0u; };
+  auto head = [&](int slot) -> uint32_t { return lane < 6 ? __ldcg(a.recs + (size_t)slot * REC_WORDS + lane) : 0u; };
 
   while (true) {
     bool found = false;
@@ -634,9 +674,15 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
       int sl = -1;
       if (active) {
         const int pos = t >> 1, dir = t & 1;
-        const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
-        sl = tbl_find(a, dir ? fwd : revcomp(fwd, k));
-        const uint32_t f = flag_byte(a, s0 + pos);
+        uint32_t f;
+        if (FAST) {
+          sl = c.S->slot[2 * (rel + pos) + dir];
+          f = c.S->flag[rel + pos];
+        } else {
+          const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
+          sl = tbl_find(a, dir ? fwd : revcomp(fwd, k));
+          f = flag_byte(a, s0 + pos);
+        }
         known = sl >= 0;
         spc = t - last_junc_pos >= 2 * a.spacer - 1;
         cnt = dir ? (f >> 3) & 3u : (f >> 5) & 3u;
@@ -662,13 +708,18 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
     if (!found) break;
     if (slot < 0) return false;  // a junction would be created here
     const int pos = tp >> 1, dir = tp & 1;
-    const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
-    const uint64_t key = dir ? fwd : revcomp(fwd, k);
-    const int real = dir ? (int)code_at_t<false>(a.packed, s0 + pos + k) : (int)nt_comp(code_at_t<false>(a.packed, s0 + pos - 1));
+    const int real = dir ? (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base)
+                         : (int)nt_comp(code_at_t<FAST>(c.pk, s0 + pos - 1 - c.pk_base));
     const int fwd_idx = dir ? real : 4, back_idx = dir ? 4 : real;
-    const uint32_t hd = head(slot);
-    const uint32_t d_fwd = __shfl_sync(0xffffffffu, hd, fwd_idx), d_back = __shfl_sync(0xffffffffu, hd, back_idx);
-    const uint32_t link = __shfl_sync(0xffffffffu, hd, REC_LINK);
+    uint32_t d_fwd, d_back, link;
+    if (FAST) {
+      const int hs = 2 * (rel + pos) + dir;
+      d_fwd = c.S->hop[hs]; d_back = c.S->dback[hs]; link = c.S->lnk[hs];
+    } else {
+      const uint32_t hd = head(slot);
+      d_fwd = __shfl_sync(0xffffffffu, hd, fwd_idx); d_back = __shfl_sync(0xffffffffu, hd, back_idx);
+      link = __shfl_sync(0xffffffffu, hd, REC_LINK);
+    }
     if (have_last) {
       const uint32_t dv = (uint32_t)(tp - last_tp) & 0xffu;
       if (dv > last_dist_fwd || dv > d_back || !((last_link >> last_fwd_idx) & 1u) || !((link >> back_idx) & 1u)) return false;
@@ -678,24 +729,35 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
     if (!land(slot, real)) return false;
     const int dist = d_fwd < 1u ? 1 : (int)d_fwd;
     if (lane == 0) { c.cnt[SS_PROCESSED] += 1; c.cnt[SS_SKIPPED] += (unsigned long long)(dist - 1); }
-    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
+    if (pairs || want_ext) {
+      const uint64_t fwd = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
+      out_push(a, c, o, ext_fwd(dir ? fwd : revcomp(fwd, k), (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
+    }
     have_last = true;
     last_junc_pos = tp; last_tp = tp; last_fwd_idx = fwd_idx; last_dist_fwd = d_fwd; last_link = link;
     tp += dist;
   }
   if (!have_last) {  // the fake mid-read junction must already be there, with distances at least as long
     const int pos = len / 2 - k / 2;
-    const uint64_t key = kmer_at_t<false>(a.packed, s0 + pos, k);
-    const int real = (int)code_at_t<false>(a.packed, s0 + pos + k);
-    const int slot = tbl_find(a, key);
+    const uint64_t key = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
+    const int real = (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base);
+    int slot;
+    uint32_t have4, have_real;  // its dist[4] and dist[real]
+    if (FAST) {
+      const int hs = 2 * (rel + pos) + 1;
+      slot = c.S->slot[hs]; have4 = c.S->dback[hs]; have_real = c.S->hop[hs];
+    } else {
+      slot = tbl_find(a, key);
+      const uint32_t hd = slot >= 0 ? head(slot) : 0u;
+      have4 = __shfl_sync(0xffffffffu, hd, 4); have_real = __shfl_sync(0xffffffffu, hd, real);
+    }
     if (slot < 0) return false;
-    const uint32_t hd = head(slot);
     const int mtp = 2 * pos + 1;
     const uint32_t d4 = (uint32_t)(mtp - 2 * j) & 0xffu, dr = (uint32_t)((2 * len - mtp - 2 * k + 1) - 2 * j) & 0xffu;
-    if (d4 > __shfl_sync(0xffffffffu, hd, 4) || dr > __shfl_sync(0xffffffffu, hd, real)) return false;
+    if (d4 > have4 || dr > have_real) return false;
     if (!land(slot, real)) return false;
     if (lane == 0) c.cnt[SS_NOJUNC]++;
-    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
+    if (pairs || want_ext) out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
   } else if (((uint32_t)((2 * len - last_tp - 2 * k + 1) - 2 * j) & 0xffu) > last_dist_fwd) {
     return false;
   }
@@ -760,7 +822,7 @@ __device__ bool scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
           bit += __ffs(x) - 1;
           const int run_len = base + bit - run_start;
           if (run_len >= k) {
-            if (DRY) { if (!dry_forward(a, c, ss + run_start, run_len + k - 1, lane)) return false; }
+            if (DRY) { if (!dry_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane)) return false; }
             else scan_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane);
             if (lane == 0) c.cnt[SS_NOERR]++;
           }
@@ -772,23 +834,53 @@ __device__ bool scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
   return true;
 }
 
-// phase 1: everything the walk will want to know about the line, all loads in flight together
+// phase 1: everything the walk will want to know about the line, all loads in flight together.
+// n_runs >= 0: S->reskey[0 .. n_runs) lists the line's minimizer runs (slot | first position << 24, in position order);
+// a run whose slot has no junction at all (a.jslot) cannot hold a junction key, so its positions are not looked up.
+// n_runs < 0: every position is looked up.
 template <int PF>  // positions per lane per pass
-__device__ void prefetch_line(const StitchArgs& a, WarpScratch* S, uint32_t ls, int n_pos, int lane) {
+__device__ void prefetch_line(const StitchArgs& a, WarpScratch* S, uint32_t ls, int n_pos, int lane, int n_runs) {
   const int k = a.k;
-  for (int base = 0; base < n_pos; base += 32 * PF) {
+  for (int i = lane; i < 2 * n_pos; i += 32) S->slot[i] = -1;
+  int n_list = n_pos;
+  if (n_runs >= 0) {
+    if (lane < POS_CAP / 32) S->pmask[lane] = 0u;
+    __syncwarp();
+    for (int c = lane; c < n_runs; c += 32) {
+      const uint32_t e = S->reskey[c], sl = e & ROW_SLOT_MASK;
+      if ((__ldcg(a.jslot + (sl >> 5)) >> (sl & 31u)) & 1u) {
+        const int st = (int)(e >> 24), en = c + 1 < n_runs ? (int)(S->reskey[c + 1] >> 24) : n_pos;
+        for (int w = st >> 5; w <= (en - 1) >> 5 && en > st; w++) {
+          const int lo = st > 32 * w ? st - 32 * w : 0, hi = en < 32 * w + 32 ? en - 32 * w : 32;  // bits [lo, hi) of word w
+          atomicOr(&S->pmask[w], (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u));
+        }
+      }
+    }
+    __syncwarp();
+    n_list = 0;
+    for (int base = 0; base < n_pos; base += 32) {
+      const int pos = base + lane;
+      const bool on = pos < n_pos && ((S->pmask[base >> 5] >> lane) & 1u);
+      const uint32_t b = __ballot_sync(0xffffffffu, on);
+      if (on) S->plist[n_list + __popc(b & ((1u << lane) - 1u))] = (uint8_t)pos;
+      n_list += __popc(b);
+    }
+    __syncwarp();
+  }
+  for (int base = 0; base < n_list; base += 32 * PF) {
     uint64_t fwd[PF], rcv[PF];
     unsigned long long kf[PF], kb[PF];
     uint64_t hf[PF], hb[PF];
+    int ps[PF];
 #pragma unroll
     for (int i = 0; i < PF; i++) {
-      const int pos = base + 32 * i + lane;
-      if (pos < n_pos) fwd[i] = kmer_at_t<true>(S->pk, (ls & 15u) + pos, k);
+      const int idx = base + 32 * i + lane;
+      ps[i] = idx < n_list ? (n_runs >= 0 ? (int)S->plist[idx] : idx) : -1;
+      if (ps[i] >= 0) fwd[i] = kmer_at_t<true>(S->pk, (ls & 15u) + ps[i], k);
     }
 #pragma unroll
     for (int i = 0; i < PF; i++) {
-      const int pos = base + 32 * i + lane;
-      if (pos < n_pos) {
+      if (ps[i] >= 0) {
         rcv[i] = revcomp(fwd[i], k);
         hf[i] = mix64(fwd[i]) & (a.cap - 1); hb[i] = mix64(rcv[i]) & (a.cap - 1);
         kf[i] = __ldcg(a.keys + hf[i]); kb[i] = __ldcg(a.keys + hb[i]);
@@ -796,8 +888,8 @@ __device__ void prefetch_line(const StitchArgs& a, WarpScratch* S, uint32_t ls, 
     }
 #pragma unroll
     for (int i = 0; i < PF; i++) {
-      const int pos = base + 32 * i + lane;
-      if (pos < n_pos) {
+      const int pos = ps[i];
+      if (pos >= 0) {
         int sf, sb;
         if (fwd[i] == KEY_EMPTY) sf = tbl_find(a, fwd[i]);
         else {
@@ -809,12 +901,28 @@ __device__ void prefetch_line(const StitchArgs& a, WarpScratch* S, uint32_t ls, 
           while (kb[i] != rcv[i] && kb[i] != KEY_EMPTY) { hb[i] = (hb[i] + 1) & (a.cap - 1); kb[i] = __ldcg(a.keys + hb[i]); }
           sb = kb[i] == rcv[i] ? (int)hb[i] : -1;
         }
-        S->kmer[pos] = fwd[i];
         S->slot[2 * pos + 1] = sf;
         S->slot[2 * pos] = sb;
-        // dist[fwdIdx]: facing forward fwdIdx = the read's next base, facing backward fwdIdx = 4
-        if (sf >= 0) S->hop[2 * pos + 1] = (uint8_t)__ldcg(rec_field(a, sf, REC_DIST + (int)code_at_t<true>(S->pk, (ls & 15u) + pos + k)));
-        if (sb >= 0) S->hop[2 * pos] = (uint8_t)__ldcg(rec_field(a, sb, REC_DIST + 4));
+        // facing forward: fwdIdx = the read's next base, backIdx = 4; facing backward: fwdIdx = 4, backIdx = complement
+        // of the base before the k-mer (utils/ReadKmer.cpp:95-114).  dist[0..4] and the link mask share one 32-byte sector.
+        if (sf >= 0) {
+          const uint32_t* r = rec_field(a, sf, 0);
+          const uint4 d03 = __ldcg(reinterpret_cast<const uint4*>(r));
+          const uint2 d45 = __ldcg(reinterpret_cast<const uint2*>(r + 4));
+          const uint32_t real = code_at_t<true>(S->pk, (ls & 15u) + pos + k);
+          S->hop[2 * pos + 1] = (uint8_t)(real == 0 ? d03.x : real == 1 ? d03.y : real == 2 ? d03.z : d03.w);
+          S->dback[2 * pos + 1] = (uint8_t)d45.x;
+          S->lnk[2 * pos + 1] = (uint8_t)d45.y;
+        }
+        if (sb >= 0) {
+          const uint32_t* r = rec_field(a, sb, 0);
+          const uint4 d03 = __ldcg(reinterpret_cast<const uint4*>(r));
+          const uint2 d45 = __ldcg(reinterpret_cast<const uint2*>(r + 4));
+          const uint32_t back = pos ? nt_comp(code_at_t<true>(S->pk, (ls & 15u) + pos - 1)) : 0u;
+          S->hop[2 * pos] = (uint8_t)d45.x;
+          S->dback[2 * pos] = (uint8_t)(back == 0 ? d03.x : back == 1 ? d03.y : back == 2 ? d03.z : d03.w);
+          S->lnk[2 * pos] = (uint8_t)d45.y;
+        }
       }
     }
   }
@@ -865,14 +973,14 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
       fast = n_pos > 0 && n_pos <= POS_CAP;
       if (fast) {
         // one coalesced sweep fetches everything the line needs from the planes
-        if (lane < 24) S->pk[lane] = __ldg(a.packed + (ls >> 4) + lane);
-        if (lane < 12) S->inv[lane] = __ldg(a.inval + (ls >> 5) + lane);
+        if (lane < PK_WORDS) S->pk[lane] = __ldg(a.packed + (ls >> 4) + lane);
+        if (lane < INV_WORDS) S->inv[lane] = __ldg(a.inval + (ls >> 5) + lane);
         for (int pos = lane; pos < n_pos; pos += 32) S->flag[pos] = a.flags[ls + pos];
         __syncwarp();
         const unsigned long long ta = gtime_ns();
         line_reservations<0, true>(a, S->pk, ls & 15u, len, rec, lane, S->reskey, &n_res);
         const unsigned long long tb = gtime_ns();
-        prefetch_line<(MIN_BLOCKS >= 4 ? 1 : 2)>(a, S, ls, n_pos, lane);
+        prefetch_line<(MIN_BLOCKS >= 4 ? 1 : 2)>(a, S, ls, n_pos, lane, n_res <= RES_CAP ? n_res : -1);
         if (gw == 0 && lane == 0) { S->st[SS_T_P1A] += ta - t0; S->st[SS_T_P1B] += tb - ta; S->st[SS_T_P1C] += gtime_ns() - tb; }
       } else {
         line_reservations<0, false>(a, a.packed, ls, len, rec, lane, S->reskey, &n_res);
@@ -893,11 +1001,11 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
       if (n_res <= RES_CAP) {
         bool ok = true;
         for (int i = lane; i < n_res; i += 32)
-          if (__ldcg(a.res + S->reskey[i]) != rec) ok = false;
+          if (__ldcg(a.res + (S->reskey[i] & ROW_SLOT_MASK)) != rec) ok = false;
         mine = __all_sync(0xffffffffu, ok);
         // (release after the whole check: two runs of a line may hash to the same slot)
         for (int i = lane; i < n_res; i += 32)
-          if (__ldcg(a.res + S->reskey[i]) == rec) __stcg(a.res + S->reskey[i], RES_FREE);
+          if (__ldcg(a.res + (S->reskey[i] & ROW_SLOT_MASK)) == rec) __stcg(a.res + (S->reskey[i] & ROW_SLOT_MASK), RES_FREE);
       } else {
         mine = line_reservations<1, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
         line_reservations<2, false>(a, a.packed, ls, len, rec, lane, nullptr, nullptr);
@@ -942,56 +1050,111 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
 }
 
 // ---- epochs: the read-only walk, the verify step, the exact-set list ------------------------------
-struct DryScratch {  // shared memory of one warp of the read-only kernels
-  unsigned long long stage[EXT_STAGE];
-  unsigned long long st[SS_COUNT];   // the warp's totals, flushed when the kernel ends
+struct DryScratch {  // shared memory of one warp of the read-only kernel
+  WarpScratch W;                     // the line's planes, flags and parked lookups; W.st = the warp's totals
   unsigned long long cnt[SS_WALK];   // the current record's counters
   uint32_t land_slot[LAND_CAP];
   uint8_t land_nt[LAND_CAP];
 };
 
-// DRY_CLASSIFY: every record of [r_begin, r_end) walks against the snapshot; in_exact[rec] := 1 when it is not quiet.
-// DRY_APPLY:    the records with in_exact == 0 walk again (same snapshot, same walk) and commit: coverage counts into
-//               the live table, scan counters, pair-filter adds and extension lists.
-__global__ void __launch_bounds__(DRY_THREADS) stitch_dry_kernel(StitchArgs a) {
-  __shared__ DryScratch scratch[DRY_WARPS];
-  DryScratch* S = scratch + (threadIdx.x >> 5);
+// DRY_CLASSIFY        every record of [r_begin, r_end) walks against the table in a.keys / a.recs (nothing of it that a
+//                     walk reads changes meanwhile); in_exact[rec] := EX_MEMBER when it is not quiet; its reservation
+//                     slots go to a.rows for the verify step.
+// DRY_CLASSIFY_APPLY  the same, and a quiet record commits at once: coverage counts into cov_out, scan counters.
+// DRY_APPLY           the records with in_exact == want_flag walk again and commit, pair-filter adds and extension
+//                     lists included.
+// DRY_RETRACT         the records with in_exact == want_flag walk again and take their commit back (cov_out, and
+//                     cov_out2 / st2 when given); in_exact := flag_after.
+// DRY_RECHECK         the records with in_exact == want_flag walk (the caller points a.keys / a.recs at the live table):
+//                     quiet -> EX_SETTLED, else -> taint_mark (they join the exact set).
+__global__ void __launch_bounds__(DRY_THREADS, 3) stitch_dry_kernel(StitchArgs a) {
+  extern __shared__ __align__(16) unsigned char stitch_smem[];
+  DryScratch* S = reinterpret_cast<DryScratch*>(stitch_smem) + (threadIdx.x >> 5);
+  WarpScratch* W = &S->W;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * DRY_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * DRY_THREADS) >> 5;
-  if (lane < SS_COUNT) S->st[lane] = 0;
+  if (lane < SS_COUNT) W->st[lane] = 0;
   __syncwarp();
   WarpCtx c;
-  c.S = nullptr; c.stage = S->stage; c.cnt = S->cnt; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0;
-  c.n_pos = 0; c.n_vis = 0; c.stamp = 0; c.wrote = false; c.land_slot = S->land_slot; c.land_nt = S->land_nt;
+  c.S = W; c.stage = W->stage; c.cnt = S->cnt; c.n_vis = 0; c.stamp = 0; c.wrote = false;
+  c.land_slot = S->land_slot; c.land_nt = S->land_nt;
   c.emit = a.dry_mode == DRY_APPLY;
+  const int mode = a.dry_mode;
+  const bool classify = mode == DRY_CLASSIFY || mode == DRY_CLASSIFY_APPLY;
   for (uint32_t rec = a.r_begin + gw; rec < a.r_end; rec += n_warps) {
-    if (a.dry_mode == DRY_APPLY && a.in_exact[rec]) continue;
+    if (!classify && a.in_exact[rec] != a.want_flag) continue;
     const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
-    if (le <= ls) continue;
+    const uint32_t len = le > ls ? le - ls : 0u;
+    const int n_pos = len >= (uint32_t)a.k ? (int)(len - a.k + 1) : 0;
+    const bool fast = n_pos > 0 && n_pos <= POS_CAP;
+    uint32_t* row = classify ? a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS : nullptr;
     c.rec = rec; c.part = 0; c.n_stage = 0; c.n_land = 0; c.ls = ls;
     if (lane < SS_WALK) S->cnt[lane] = 0;
+    bool quiet = true;
+    if (fast) {
+      if (lane < PK_WORDS) W->pk[lane] = __ldg(a.packed + (ls >> 4) + lane);
+      if (lane < INV_WORDS) W->inv[lane] = __ldg(a.inval + (ls >> 5) + lane);
+      for (int pos = lane; pos < n_pos; pos += 32) W->flag[pos] = a.flags[ls + pos];
+      __syncwarp();
+      int n_res = 0;
+      if (classify) {
+        line_reservations<3, true>(a, W->pk, ls & 15u, len, rec, lane, W->reskey, &n_res, ROW_WORDS - 1);
+        __syncwarp();
+        if (lane == 0) row[0] = n_res < ROW_WORDS ? (uint32_t)n_res : 255u;
+        if (lane + 1 < ROW_WORDS && lane < n_res) row[1 + lane] = W->reskey[lane];
+      } else {  // the row classify left
+        const uint32_t* rr = a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS;
+        n_res = (int)__ldg(rr);
+        if (lane + 1 < ROW_WORDS && lane < n_res) W->reskey[lane] = __ldg(rr + 1 + lane);
+        __syncwarp();
+      }
+      prefetch_line<2>(a, W, ls, n_pos, lane, n_res < ROW_WORDS ? n_res : -1);
+      c.n_pos = n_pos; c.pk = W->pk; c.pk_base = ls & ~15u; c.inv = W->inv; c.inv_base = ls & ~31u;
+      quiet = scan_line<true, true>(a, c, ls, le, lane);
+    } else {
+      if (classify && lane == 0) row[0] = len ? 255u : 0u;
+      if (len) {
+        __syncwarp();
+        c.n_pos = 0; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0;
+        quiet = scan_line<false, true>(a, c, ls, le, lane);
+      }
+    }
     __syncwarp();
-    const bool quiet = scan_line<false, true>(a, c, ls, le, lane);
-    __syncwarp();
-    if (a.dry_mode == DRY_CLASSIFY) {
-      if (!quiet && lane == 0) { a.in_exact[rec] = 1; S->st[SS_NONQUIET]++; }
+    if (mode == DRY_RECHECK) {
+      if (lane == 0) a.in_exact[rec] = quiet ? (uint8_t)EX_SETTLED : a.taint_mark;
       continue;
     }
-    if (!quiet) {  // cannot happen: apply repeats the walk classify found quiet
-      if (lane == 0) S->st[SS_DRY_ERROR]++;
+    if (!quiet) {
+      if (classify) { if (lane == 0) { a.in_exact[rec] = EX_MEMBER; W->st[SS_NONQUIET]++; } }
+      else if (lane == 0) W->st[SS_DRY_ERROR]++;  // cannot happen: the walk that was found quiet is repeated
       c.n_stage = 0;
       continue;
     }
-    for (int i = lane; i < c.n_land; i += 32)
-      atomicAdd(a.cov_out + (size_t)S->land_slot[i] * REC_WORDS + REC_COV + S->land_nt[i], 1u);
-    if (lane < SS_WALK) S->st[lane] += S->cnt[lane];
+    if (mode == DRY_CLASSIFY) continue;
+    const uint32_t one = mode == DRY_RETRACT ? 0xffffffffu : 1u;
+    for (int i = lane; i < c.n_land; i += 32) {
+      const size_t w = (size_t)S->land_slot[i] * REC_WORDS + REC_COV + S->land_nt[i];
+      atomicAdd(a.cov_out + w, one);
+      if (mode == DRY_RETRACT && a.cov_out2) atomicAdd(a.cov_out2 + w, one);
+    }
+    if (lane < SS_WALK) { if (mode == DRY_RETRACT) W->st[lane] -= S->cnt[lane]; else W->st[lane] += S->cnt[lane]; }
+    if (mode == DRY_RETRACT && lane == 0) a.in_exact[rec] = a.flag_after;
     if (a.ext && c.n_stage) ext_flush(a, c, lane);
   }
   __syncwarp();
-  if (lane < SS_COUNT && S->st[lane]) atomicAdd(&a.st->stats[lane], S->st[lane]);
+  if (lane < SS_COUNT && W->st[lane]) {
+    atomicAdd(&a.st->stats[lane], W->st[lane]);
+    if (mode == DRY_RETRACT && a.st2) atomicAdd(&a.st2->stats[lane], W->st[lane]);
+  }
 }
 
-// A record outside the exact set whose line touches a slot that an EARLIER record wrote joins the set.
+// Which records outside the exact set may have seen something else than T0?  dirty[] / dirty_max[] hold, per
+// reservation slot, the first / last record of the exact set that wrote a junction under that slot in the run
+// that just ended.  For a record R:
+//   no write before R under any of its slots      -> T0 is what it would have seen                     (EX_QUIET)
+//   writes before R, none after R                 -> the LIVE table is what it would have seen on its keys: it is
+//                                                    walked again there                                (EX_RECHECK)
+//   writes before and after R                     -> it joins the exact set                            (taint_mark)
 __global__ void __launch_bounds__(DRY_THREADS) stitch_verify_kernel(StitchArgs a) {
   __shared__ uint32_t keep_s[DRY_WARPS][RES_CAP];
   uint32_t* keep = keep_s[threadIdx.x >> 5];
@@ -999,30 +1162,56 @@ __global__ void __launch_bounds__(DRY_THREADS) stitch_verify_kernel(StitchArgs a
   const uint32_t gw = (blockIdx.x * DRY_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * DRY_THREADS) >> 5;
   unsigned long long added = 0;
   for (uint32_t rec = a.r_begin + gw; rec < a.r_end; rec += n_warps) {
-    if (a.in_exact[rec]) continue;
-    const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
-    if (le <= ls || le - ls < (uint32_t)a.k) continue;
-    int n = 0;
-    line_reservations<3, false>(a, a.packed, ls, le - ls, rec, lane, keep, &n);
-    __syncwarp();
-    bool hit = n > RES_CAP;  // (a line with more slots than fit is taken by the ordered kernel)
-    for (int i = lane; i < n && i < RES_CAP; i += 32)
-      if (__ldcg(a.dirty + keep[i]) < rec) hit = true;
-    hit = __any_sync(0xffffffffu, hit);
-    if (hit && lane == 0) { a.in_exact[rec] = 1; added++; }
-    __syncwarp();
+    const uint8_t fl = a.in_exact[rec];
+    if (fl != EX_QUIET && fl != EX_SETTLED) continue;
+    const uint32_t* row = a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS;
+    const uint32_t n_row = __ldg(row);
+    bool before = false, after = false;
+    if (n_row < ROW_WORDS) {
+      if (lane < (int)n_row) {
+        const uint32_t sl = __ldg(row + 1 + lane) & ROW_SLOT_MASK;
+        before = __ldcg(a.dirty + sl) < rec;
+        after = __ldcg(a.dirty_max + sl) > rec + 1u;
+      }
+    } else {  // more slots than a row holds: list them again
+      const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
+      int n = 0;
+      line_reservations<3, false>(a, a.packed, ls, le - ls, rec, lane, keep, &n);
+      __syncwarp();
+      if (n > RES_CAP) before = after = true;  // (and more than fit here: the ordered kernel takes the line)
+      for (int i = lane; i < n && i < RES_CAP; i += 32) {
+        before |= __ldcg(a.dirty + (keep[i] & ROW_SLOT_MASK)) < rec;
+        after |= __ldcg(a.dirty_max + (keep[i] & ROW_SLOT_MASK)) > rec + 1u;
+      }
+      __syncwarp();
+    }
+    before = __any_sync(0xffffffffu, before);
+    after = __any_sync(0xffffffffu, after);
+    uint8_t nf = EX_QUIET;
+    if (before) nf = (after || !a.recheck) ? a.taint_mark : (uint8_t)EX_RECHECK;
+    if (lane == 0 && nf != fl) a.in_exact[rec] = nf;
+    if (lane == 0 && before && nf == a.taint_mark) added++;
   }
   if (lane == 0 && added) atomicAdd(&a.st->stats[SS_TAINTED], added);
 }
 
 // in_exact flags of [r_begin, r_end) -> 0/1 counts (then exclusive prefix sum, then the ascending list)
 __global__ void exact_flags_kernel(const uint8_t* __restrict__ in_exact, uint32_t r_begin, uint32_t n, uint32_t* __restrict__ out) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in_exact[r_begin + i] ? 1u : 0u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint8_t f = in_exact[r_begin + i];
+    out[i] = (f >= EX_MEMBER && f <= EX_RETRACTED) ? 1u : 0u;
+  }
+}
+// fallback of an epoch that applied at classify time: every record that committed is queued for retraction
+__global__ void exact_mark_applied_kernel(uint8_t* __restrict__ in_exact, uint32_t r_begin, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (in_exact[r_begin + i] == EX_QUIET || in_exact[r_begin + i] >= EX_SETTLED) in_exact[r_begin + i] = EX_COMMITTED;
 }
 __global__ void exact_list_kernel(const uint8_t* __restrict__ in_exact, uint32_t r_begin, uint32_t n,
                                   const uint32_t* __restrict__ prefix, uint32_t* __restrict__ list, uint32_t* __restrict__ count_out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const bool in = in_exact[r_begin + i] != 0;
+    const uint8_t f = in_exact[r_begin + i];
+    const bool in = f >= EX_MEMBER && f <= EX_RETRACTED;
     if (in) list[prefix[i]] = r_begin + i;
     if (i == n - 1) *count_out = prefix[i] + (in ? 1u : 0u);
   }

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <sstream>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -173,19 +174,44 @@ bool write_junctions(const std::string& path, const faucet_junction_rec* recs, u
   return true;
 }
 
+// JunctionMap::buildFromFile (utils/JunctionMap.cpp:619-639) + Junction::Junction(string) (utils/Junction.cpp:102-118):
+// "KMER d0..d4  c0..c3 csum  l0..l4 " per line; a later line with the same k-mer replaces the earlier one.
+bool read_junctions(const std::string& path, int k, std::unordered_map<uint64_t, Junction>& map) {
+  std::ifstream f(path);
+  printf("Reading from Junction file to build junction map.\n");
+  std::string line, word;
+  while (std::getline(f, line)) {
+    std::istringstream iss(line);
+    iss >> word;
+    if ((int)word.size() < k) continue;
+    uint64_t kmer = 0;  // getFirstKmerFromRead: A=0 C=1 T=2 G=3 (utils/Kmer.cpp:82-88, 429-433)
+    for (int i = 0; i < k; i++) kmer = (kmer << 2) | (uint64_t)((word[i] >> 1) & 3);
+    Junction j;
+    int v = 0;
+    for (int i = 0; i < 5; i++) { iss >> v; j.dist[i] = (uint8_t)v; }
+    for (int i = 0; i < 4; i++) { iss >> v; j.cov[i] = (uint8_t)v; }
+    iss >> v;  // the coverage sum
+    for (int i = 0; i < 5; i++) { iss >> v; j.linked[i] = v != 0; }
+    map[kmer] = j;
+  }
+  return true;
+}
+// Bloom::load (utils/Bloom.cpp:580-587): raw bytes, unchecked there
+void load_file(const std::string& path, std::vector<uint8_t>& bits) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (f) { size_t got = fread(bits.data(), 1, bits.size(), f); (void)got; fclose(f); }
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
   Options o;
   if (handle_arguments(argc, argv, o) == 1) return 1;
   if (o.mercy) { fprintf(stderr, "faucet: --mercy is not offloaded (run the reference for that flag)\n"); return 1; }
-  if (o.from_junctions) {
-    fprintf(stderr, "faucet: -junctions_file restarts AFTER both streaming passes: nothing left for this binary; "
-                    "hand the files to the reference's graph stage\n");
-    return 1;
+  if (!(o.from_bloom && o.from_junctions)) {  // (that restart skips both passes: no device work)
+    if (faucet_gpu_init(o.device)) die("init");
+    printf("Device path: %s\n", faucet_gpu_version());
   }
-  if (faucet_gpu_init(o.device)) die("init");
-  printf("Device path: %s\n", faucet_gpu_version());
 
   // ---- Bloom filter: from reads (pass 1) or from a file ------------------------------------------
   int log2_tai = 0, n_hash = 0;
@@ -227,6 +253,20 @@ int main(int argc, char* argv[]) {
     lpf.assign(((size_t)1 << l_log2) / 8, 0);
   }
   if (o.just_load) return 0;
+
+  // ---- restart after both passes (src/Faucet.cpp:289-293): JunctionMap::buildFromFile + Bloom::load of the pair filters.
+  // Both streaming passes are skipped, so there is no device work; what is left is the reference's graph stage.
+  if (o.from_junctions) {
+    std::unordered_map<uint64_t, Junction> map;
+    if (!read_junctions(o.junctions_prefix + ".junctions", o.size_kmer, map)) return 2;
+    load_file(o.junctions_prefix + ".short_pair_filter", spf);
+    if (o.paired_ends) load_file(o.junctions_prefix + ".long_pair_filter", lpf);
+    printf("Weight of short pair filter: %f\n", weight(spf));
+    if (o.paired_ends) printf("Weight of long pair filter: %f\n", weight(lpf));
+    printf("Number of junctions: %llu\n", (unsigned long long)map.size());
+    printf("Junction map and pair filters read back; contig graph construction is the reference's host stage.\n");
+    return 0;
+  }
 
   // ---- pass 2 (buildJunctionMapFromReads, src/Faucet.cpp:240-246) ---------------------------------
   faucet_junction_rec* recs = nullptr;

@@ -126,10 +126,13 @@ int faucet_gpu_set_batch_bytes(size_t bytes);
 int faucet_gpu_set_epoch_limit(uint64_t stamps);
 int faucet_gpu_get_timings(faucet_timings* out);
 /* Knobs (none changes a result; tests use them to force every code path).  Setting one drops the cached session.
- *  stitch:  "epoch_mode" 1 = adaptive epochs (default: ordered kernel while most records write, then read-only classify /
+ *  stitch:  "stitch_exec" 1 = the ordered part runs as a dataflow (per-slot predecessor lists, no grid barrier; default),
+ *           0 = in rounds of windowed reservations; "flow_chunk" records per dependency sort;
+ *           "epoch_mode" 1 = adaptive epochs (default: ordered kernel while most records write, then read-only classify /
  *           ordered exact set / verify / apply), 0 = one ordered run per batch, 2 = classify epochs from the first record;
  *           "epoch0" / "epoch_max" first / largest epoch in records; "epoch_switch_pct", "epoch_shrink_pct",
- *           "epoch_grow_pct" the thresholds of the epoch controller; "table_cap0" initial junction-table slots (power of
+ *           "epoch_grow_pct" the thresholds of the epoch controller; "epoch_recheck" 1 = a record with earlier but no later
+ *           writes under its slots is walked again on the live table (default), 0 = it joins the exact set; "table_cap0" initial junction-table slots (power of
  *           two, grows by rehash at load 1/2); "res_log2" log2 of the reservation-table entries; "stitch_w0" /
  *           "stitch_w_max" initial / maximal records per round; "stitch_shrink_den" / "stitch_grow_den" window
  *           adaptation; "stitch_blocks" resident CTAs per SM (2..4); "ext_cap0" u64 words of the extension-list buffer
@@ -176,7 +179,8 @@ int faucet_session_timer_start(faucet_session* s);
 int faucet_session_timer_stop_ms(faucet_session* s, float* ms_out);
 uint64_t faucet_session_kernel_launches(faucet_session* s);
 /* event-timed duration (ms) accumulated per named kernel since the last reset:
- * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch (ordered kernel) 5=stitch_dry (read-only walk, verify, exact-set list) */
+ * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch (ordered kernel) 5=stitch_dry (read-only walks) 6=stitch_verify (verify + exact-set list)
+ * 7=stitch_flow_prep (dependency sort of the dataflow executor) */
 int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64_t* launches_out);
 
 /* ---- multi-GPU: one process per GPU of one NVSwitch box, peer HBM mapped through CUDA IPC -----

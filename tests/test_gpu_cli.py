@@ -56,3 +56,66 @@ def test_cli_restart_from_bloom_file(tmp_path):
     ref2 = _run(REF_BIN, reads, str(tmp_path / "ref2"), base + ["-bloom_file", str(tmp_path / "ref.bloom")])
     assert ours.returncode == 0, ours.stderr
     assert filecmp.cmp(str(tmp_path / "ours.junctions"), str(tmp_path / "ref2.junctions"), shallow=False)
+
+
+DROPIN = os.path.join(ROOT, "faucet_b200", "bin", "faucet_dropin")
+ALL_FILES = [".bloom", ".junctions", ".short_pair_filter", ".long_pair_filter", ".cleaned_contigs.fasta",
+             ".cleaned_graph_unitigs.fastg"]
+
+
+def _run2(exe, reads, prefix, k, max_len, est, sing, extra, timeout=900):
+    cmd = [exe, "-read_load_file", reads, "-read_scan_file", reads, "-size_kmer", str(k), "-max_read_length", str(max_len),
+           "-estimated_kmers", str(est), "-singletons", str(sing), "-file_prefix", prefix] + extra
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+
+
+def _same_files(tmp_path, suffixes, ref):
+    for suf in suffixes:
+        a, b = str(tmp_path / "ours") + suf, str(tmp_path / "ref") + suf
+        assert os.path.exists(b), f"reference wrote no {suf}: {ref.stdout[-500:]} {ref.stderr[-500:]}"
+        assert os.path.exists(a), f"no {suf} from the GPU path"
+        assert os.path.getsize(a) > 0 and filecmp.cmp(a, b, shallow=False), f"{suf} differs from the reference's file"
+
+
+@pytest.mark.parametrize("extra,suffixes", [
+    (["--fastq", "--paired_ends"], ALL_FILES),                       # cleaning on: pair filters, contigs, unitig graph
+    (["--fastq", "--paired_ends", "--no_cleaning"], ALL_FILES[:2]),
+    (["--fastq", "-j", "0", "-max_spacer_dist", "40"], [s for s in ALL_FILES if s != ".long_pair_filter"]),
+])
+def test_dropin_binary_reproduces_reference_contigs(tmp_path, extra, suffixes):
+    """faucet_dropin = the reference's OWN main() and graph stage (compiled unmodified) linked against
+    faucet_b200/host/dropin/adaptors.cpp, which runs load_two_filters and ReadScanner::scanReads on the GPU.
+    Planted repeats keep the reference's cleaning alive.  Every file the reference writes -- down to the
+    cleaned contigs -- must be byte-identical."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/faucet was not built")
+    assert os.path.exists(DROPIN), "faucet_b200/bin/faucet_dropin missing: run __graft_entry__.build() where /root/reference is mounted"
+    reads = gen_reads(str(tmp_path / "r.fq"), genome=200000, cov=30, length=100, insert=300, seed=61, err=0.005, repeats=True)
+    ours = _run2(DROPIN, reads, str(tmp_path / "ours"), 31, 100, 2400000, 2000000, extra)
+    assert ours.returncode == 0, ours.stderr[-2000:] + ours.stdout[-2000:]
+    ref = _run2(REF_BIN, reads, str(tmp_path / "ref"), 31, 100, 2400000, 2000000, extra)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    _same_files(tmp_path, suffixes, ref)
+    if "--no_cleaning" not in extra:
+        assert ">" in open(str(tmp_path / "ours.cleaned_contigs.fasta")).read()
+
+
+@pytest.mark.parametrize("variant", ["e0", "e5"])
+def test_config1_full_size_matches_reference_binary(tmp_path, variant):
+    """BASELINE configs[0] at full size (1 Mbp, 30x, 100 bp interleaved paired-end FASTQ, k = 31: 21 M k-mers per
+    pass), error-free and with 0.5 % errors + planted repeats: every file byte-identical to the reference binary's"""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/faucet was not built")
+    if variant == "e0":  # a repeat-free genome: the reference's cleaning dies (SURVEY F9), so stop after the graph build
+        kw, est, sing, extra, sufs, exe = {}, 1000000, 10000, ["--fastq", "--paired_ends", "--no_cleaning"], ALL_FILES[:2], CLI
+    else:
+        kw, est, sing, extra, sufs, exe = dict(err=0.005, repeats=True), 12000000, 10000000, ["--fastq", "--paired_ends"], ALL_FILES, DROPIN
+    reads = gen_reads(str(tmp_path / "c1.fq"), genome=1000000, cov=30, length=100, insert=300, seed=1, **kw)
+    ours = _run2(exe, reads, str(tmp_path / "ours"), 31, 100, est, sing, extra)
+    assert ours.returncode == 0, ours.stderr[-2000:] + ours.stdout[-2000:]
+    ref = _run2(REF_BIN, reads, str(tmp_path / "ref"), 31, 100, est, sing, extra)
+    _same_files(tmp_path, sufs, ref)
+    for key in ("Reads processed:", "Unambiguous reads:", "Number of junctions:"):
+        mine = [l for l in ours.stdout.splitlines() if l.startswith(key)]
+        theirs = [l for l in ref.stdout.splitlines() if l.startswith(key)]
+        assert mine and mine == theirs[:len(mine)], (key, mine, theirs)

@@ -42,11 +42,15 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
-EPOCH_DEFAULTS = {"epoch_mode": 1, "epoch0": 8192, "epoch_max": 1 << 20}
+EPOCH_DEFAULTS = {"epoch_mode": 1, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 20}
 EPOCH_SCHEDULES = {
     "adaptive": {},                                                     # the default: ordered epochs first, then classify epochs
-    "ordered_only": {"epoch_mode": 0},                                  # one run of the ordered kernel per batch
+    "ordered_only": {"epoch_mode": 0},                                  # one run of the ordered (dataflow) executor per batch
+    "rounds_only": {"epoch_mode": 0, "stitch_exec": 0},                 # ... of the round-based ordered kernel
+    "classify_rounds": {"epoch_mode": 2, "epoch0": 300, "epoch_max": 5000, "stitch_exec": 0},
+    "flow_small_chunks": {"epoch_mode": 1, "epoch0": 1024, "flow_chunk": 700},  # dependency sort every 700 records
     "classify_tiny": {"epoch_mode": 2, "epoch0": 192, "epoch_max": 3000},  # classify / execute / verify / apply from record 0 on
+    "classify_join": {"epoch_mode": 2, "epoch0": 500, "epoch_max": 8000, "epoch_recheck": 0},  # tainted records all join the exact set
 }
 
 
@@ -234,7 +238,7 @@ def test_stitch_schedule_is_invisible(fb, oracle, small_fq, knobs, impl):
     assert gst == ost
     assert _strip(grecs) == _strip(orecs)
     assert np.array_equal(gspf, ospf) and np.array_equal(glpf, olpf)
-    assert tim["stitch_rounds"] > 0
+    assert tim["exact_records"] > 0
 
 
 def test_stitch_repetitive_reads(fb, oracle, tmp_path_factory, impl):

@@ -27,7 +27,7 @@ dev = torch.from_numpy(raw[:n]).cuda()
 CONFIGS = [dict(), dict(epoch_mode=0)]
 if os.environ.get("SWEEP"):
     CONFIGS = [json.loads(x) for x in os.environ["SWEEP"].split(";")]
-DEFAULT = dict(epoch_mode=1, epoch0=8192, epoch_max=1 << 20, epoch_switch_pct=30, epoch_shrink_pct=14, epoch_grow_pct=6,
+DEFAULT = dict(stitch_exec=1, epoch_recheck=1, flow_chunk=1 << 20, epoch_mode=1, epoch0=8192, epoch_max=1 << 20, epoch_switch_pct=30, epoch_shrink_pct=14, epoch_grow_pct=6,
                stitch_blocks=3, stitch_shrink_den=4, stitch_grow_den=10, stitch_w_max=1 << 15, res_log2=24, table_cap0=1 << 22)
 ref = None
 for cfg in CONFIGS:
@@ -45,7 +45,7 @@ for cfg in CONFIGS:
         nj = s.stitch(True, True)
         s.sync()
         wall = (time.perf_counter() - t0) * 1e3
-        ts.append((wall, s.kernel_ms("stitch")[0], s.kernel_ms("stitch_dry")[0]))
+        ts.append((wall, s.kernel_ms("stitch")[0], s.kernel_ms("stitch_dry")[0], s.kernel_ms("stitch_verify")[0], s.kernel_ms("stitch_flow_prep")[0]))
         s.set_profiling(False)
     recs, st = s.junctions()
     t = fb.timings()
@@ -53,7 +53,7 @@ for cfg in CONFIGS:
     if ref is None:
         ref = sig
     best = min(ts)
-    print(json.dumps({"cfg": cfg, "wall_ms": round(best[0], 2), "ordered_ms": round(best[1], 2), "dry_ms": round(best[2], 2),
+    print(json.dumps({"cfg": cfg, "wall_ms": round(best[0], 2), "ordered_ms": round(best[1], 2), "dry_ms": round(best[2], 2), "verify_ms": round(best[3], 2), "flow_prep_ms": round(best[4], 2),
                       "rounds": t["stitch_rounds"], "deferred": t["stitch_deferred"],
                       "epochs": [t["epochs_exact"], t["epochs_classify"]], "exact_records": t["exact_records"], "dry_records": t["dry_records"],
                       "iterations": t["epoch_iterations"], "nonquiet": t["nonquiet_records"], "writers": t["writer_records"],
