@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- k-mers/s of the Faucet hot path (Bloom load + junction scan) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4] [--scaling weak|strong]
 
 A "step" = one pass of the hot path (parse + pass 1 load + pass 2 scan incl. stitch) over one batch of
-synthetic reads of BASELINE.json's configs[1] shape (4.6 Mbp genome, 100x, 150 bp paired-end FASTQ,
-k=31, --two_hash which is a no-op on the from-reads path).  Prints ONE JSON line (see DESIGN.md
-"Measurement" for every field).  oracle/ is used here only for the cpu_baseline / reference arm.
+synthetic reads.  Default workload = BASELINE.json configs[1] (4.6 Mbp genome, 100x, 150 bp paired-end
+FASTQ, k=31, --two_hash which is a no-op on the from-reads path).  Prints ONE JSON line (DESIGN.md
+"Measurement" explains every field).  oracle/ is used here only as the CPU baseline (cpu_baseline leg,
+--impl reference) and, at N > 1, as the checker of a small sharded job run during warm-up.
 """
 import argparse
 import ctypes
@@ -34,21 +35,30 @@ WORKLOADS = {
                desc="synthetic 1 Gbp read stream (100 Mbp genome, 10x, 100bp PE), -estimated_kmers 1e9 -singletons 2e8, k=31"),
 }
 J, MAX_SPACER, FP = 1, 100, 0.04  # faucet defaults: -j 1, -max_spacer_dist 100, -fp 0.04 (src/Faucet.h:14-48)
+METRIC = "k-mers/sec (Bloom load + junction scan)"
+KERNELS = ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry", "stitch_verify", "stitch_flow_prep")
 
 
-def gen_dataset(w, seed, pairs=None, tag="", stream=0):
+def gen_dataset(w, seed, pairs=None, tag="", stream=0, genome=None):
     """stream > 0: another read sample of the SAME genome (the shard of rank `stream` in a multi-GPU job)"""
     from _oracle import gen_reads
     d = os.environ.get("FAUCET_BENCH_TMP", "/tmp/faucet_bench")
     os.makedirs(d, exist_ok=True)
-    path = os.path.join(d, f"{w['genome']}_{w['cov']}_{w['length']}_{seed}_{stream}{tag}.fq")
+    g = genome or w["genome"]
+    path = os.path.join(d, f"{g}_{w['cov']}_{w['length']}_{seed}_{stream}{tag}.fq")
     if not os.path.exists(path):
-        kw = dict(genome=w["genome"], cov=w["cov"], length=w["length"], insert=w["insert"], seed=seed, stream=stream)
+        kw = dict(genome=g, cov=w["cov"], length=w["length"], insert=w["insert"], seed=seed, stream=stream)
         if pairs:
             kw["pairs"] = pairs
         gen_reads(path + ".tmp", **kw)
         os.replace(path + ".tmp", path)
     return path
+
+
+def config_of(w, k, lt, nh):
+    """the SAME dict in both arms (--impl ours / reference): what the metric is quoted on"""
+    return {"workload": w["desc"], "k": k, "log2_tai": lt, "n_hash": nh, "j": J, "max_spacer_dist": MAX_SPACER,
+            "fastq": True, "paired_ends": True, "no_cleaning": True}
 
 
 class ClockSampler:
@@ -100,16 +110,17 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(workload, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)"""
+    """DRAM bytes per STEP of `kernel` (all its launches of one step) from the committed ncu --set full capture
+    (profiles/ncu_traffic.json)"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p)).get(workload, {}).get(kernel, {}).get("bytes")
+        return json.load(open(p)).get(workload, {}).get(kernel, {}).get("bytes_per_step")
     except (OSError, ValueError):
         return None
 
 
-def algorithmic_bytes(w, n_hash, weight2, r_contained):
-    """SURVEY.md section 8(d) sector model, bytes per k-mer"""
+def survey_bytes(w, n_hash, weight2, r_contained):
+    """SURVEY.md section 8(d) sector model, bytes per k-mer: what the REFERENCE's algorithm moves"""
     rho = w["length"] / (w["length"] - w["k"] + 1)
     m = (1 - weight2 ** n_hash) / (1 - weight2)
     a_load = rho + 32 * n_hash * (1 + r_contained)
@@ -117,23 +128,57 @@ def algorithmic_bytes(w, n_hash, weight2, r_contained):
     return a_load, a_scan
 
 
-def cpu_reference_sample(w, k, lt, nh, path, n_reads, repeats=1):
-    """times the reference's own CPU implementation (oracle/_ref, unmodified sources) or, if it was
-    not built, the C port in oracle/ on the first n_reads reads of the workload; 1 thread (the
-    reference is single-threaded)."""
-    import numpy as np
+def kernel_bytes(w, n_hash, weight2, r_contained, text_per_kmer):
+    """algorithmic bytes per k-mer of every kernel of THIS implementation, DRAM sectors of 32 bytes
+    for every random access:
+      parse        the text in, 3/8 of it out (validity + 2-bit planes)
+      load_A/B     the planes in + one 32-byte sector of the fused {bloo1, bloo2} array per probe (SURVEY's A_load without
+                   the raw text: n (1 + r) probes)
+      scan_flags   planes in, one flag byte out per text byte, one 8-byte memo word (a 32-byte sector) per k-mer
+      stitch       planes + flags in, two 32-byte key sectors per k-mer position (both orientations), and per record
+                   its predecessor / slot rows (256 B), one done flag and ~2 record sectors per landing (~5)
+      flow_prep    ~15 (slot, record) pairs of 8 bytes per record, read and written once per radix pass (3) plus rows
+    """
+    kpr = w["length"] - w["k"] + 1  # k-mers per record
+    planes = 0.375 * text_per_kmer
+    return {
+        "parse": 1.375 * text_per_kmer,
+        "load_A": planes + 32 * n_hash * (1 + r_contained),
+        "load_B": planes,
+        "scan_flags": planes + text_per_kmer + 32.0,
+        "stitch": planes + text_per_kmer + 64.0 + (256 + 32 + 5 * 64) / kpr,
+        "stitch_dry": planes + text_per_kmer + 64.0 + (128 + 5 * 32) / kpr,
+        "stitch_verify": 128.0 / kpr,
+        "stitch_flow_prep": (planes + 15 * 8 * 2 * 3 + 256) / kpr,
+    }
+
+
+def cpu_geometry(w):
+    """Bloom geometry as the reference derives it, from oracle/_ref (or the C port): no product code in this arm"""
     from _oracle import Oracle, Ref, have_ref
-    lines = n_reads * 4
-    sample = path + f".head{n_reads}"
-    if not os.path.exists(sample):
-        with open(path, "rb") as f, open(sample, "wb") as g:
-            for _ in range(lines):
-                ln = f.readline()
-                if not ln:
-                    break
-                g.write(ln)
+    if have_ref():
+        r = Ref()
+        p1 = ctypes.c_float(r.lib.ref_brent_p1(w["est"], w["sing"], FP)).value
+        return r.geometry_optimal(w["est"], p1)
+    o = Oracle()
+    p1 = ctypes.c_float(o.lib.fo_brent_p1(w["est"], w["sing"], FP)).value
+    return o.geometry_optimal(w["est"], p1)
+
+
+def cpu_reference_sample(w, lt, nh, repeats=1):
+    """Times the reference's own CPU implementation (oracle/_ref: the unmodified sources) -- or, if it was not built,
+    the C port in oracle/ -- on a bounded sample that keeps the workload's SHAPE: same coverage, read length, insert
+    size, k, Bloom geometry and flags, over a proportionally smaller genome (so that one pass is ~10 M k-mers).
+    1 thread: the reference is single-threaded."""
+    from _oracle import Oracle, Ref, have_ref
+    k = w["k"]
+    target_kmers = int(os.environ.get("FAUCET_REF_SAMPLE_KMERS", "12000000"))
+    per_read = w["length"] - k + 1
+    genome = max(20_000, int(target_kmers / per_read * w["length"] / w["cov"]))
+    genome = min(genome, w["genome"])
+    sample = gen_dataset(w, seed=1, genome=genome, tag="_cpu")
     text = open(sample, "rb").read()
-    kmers = (text.count(b"\n") // 4) * (w["length"] - k + 1)
+    kmers = (text.count(b"\n") // 4) * per_read
     times = []
     kind = "reference" if have_ref() else "port"
     for _ in range(repeats):
@@ -147,29 +192,68 @@ def cpu_reference_sample(w, k, lt, nh, path, n_reads, repeats=1):
             _, b2, _ = o.load_two_filters(text, True, k, lt, nh)
             o.scan(text, True, True, 1, k, J, MAX_SPACER, b2, lt, nh)
         times.append(time.perf_counter() - t0)
-    return kind, kmers, times, f"first {n_reads} reads of the workload file, load+scan, --no_cleaning, full-size Bloom geometry"
+    desc = (f"{w['cov']}x {w['length']}bp paired-end reads of a {genome} bp genome ({kmers} k-mers per pass): the workload's "
+            f"coverage, read shape, k, flags and full-size Bloom geometry on a smaller genome; load_two_filters + scanReads, --no_cleaning")
+    return kind, kmers, times, desc
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import faucet_b200 as fb  # geometry only (host code); no GPU work in this arm
     k = w["k"]
-    _, lt, nh = fb.geometry_from_reads(w["est"], w["sing"], FP)
-    path = gen_dataset(w, seed=1)
-    n_reads = int(os.environ.get("FAUCET_REF_SAMPLE_READS", "60000"))
-    kind, kmers, times, sample = cpu_reference_sample(w, k, lt, nh, path, n_reads, repeats=args.steps + args.warmup)
+    lt, nh = cpu_geometry(w)
+    kind, kmers, times, sample = cpu_reference_sample(w, lt, nh, repeats=args.steps + args.warmup)
     timed = times[args.warmup:]
     val = kmers * len(timed) / sum(timed)
     print(json.dumps({
-        "impl": "reference", "metric": "k-mers/sec (Bloom load + junction scan)", "value": val, "unit": "k-mers/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "k-mers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(timed) / len(timed),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": w["desc"], "k": k, "log2_tai": lt, "n_hash": nh, "j": J},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": config_of(w, k, lt, nh),
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def sharded_parity_check(fb, torch, dist, rank, world, local):
+    """N > 1: a small stream through the SAME sharded machinery, compared bit for bit with the oracle on the whole stream"""
+    import numpy as np
+    from _oracle import Oracle, gen_reads
+    from faucet_b200.multi import ShardedJob, TorchComm
+    d = os.environ.get("FAUCET_BENCH_TMP", "/tmp/faucet_bench")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"parity_{world}.fq")
+    if rank == 0 and not os.path.exists(path):
+        gen_reads(path + ".tmp", genome=60000, cov=40, length=100, insert=300, seed=77, err=0.004, nrate=0.001, repeats=True)
+        os.replace(path + ".tmp", path)
+    dist.barrier()
+    text = open(path, "rb").read()
+    k = 31
+    _, lt, nh = fb.geometry_from_reads(60000, 30000, FP)
+    shards = fb.plan_shards(text, True, world)
+    a, b = shards[rank]
+    s = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=max(y - x for x, y in shards) + 1024)
+    job = ShardedJob(s, TorchComm(torch.device("cuda", local)))
+    job.setup()
+    s.set_text(text[a:b])
+    job.load(True)
+    g2, _ = s.get_bloom_full()
+    job.scan(True, True, True)
+    ok = True
+    o = Oracle()
+    _, o2, _ = o.load_two_filters(text, True, k, lt, nh)
+    ok &= bool(np.array_equal(g2, o2))
+    if rank == 0:
+        orecs, ost = o.scan(text, True, True, 1, k, J, MAX_SPACER, o2, lt, nh)
+        grecs, gst = s.junctions()
+        ok &= gst == ost and all(np.array_equal(grecs[f], orecs[f]) for f in ("kmer", "dist", "cov", "linked"))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    s.close_peers()
+    s.close()
+    return "ok" if int(flag.item()) == 1 else "FAILED"
 
 
 def run_ours(args, w):
@@ -193,9 +277,14 @@ def run_ours(args, w):
         fb.set_tuning(name, int(val))
     k = w["k"]
     _, lt, nh = fb.geometry_from_reads(w["est"], w["sing"], FP)
-    # weak scaling: rank g holds shard g of ONE job = N read samples (100x each) of the same genome,
-    # concatenated in rank order; the sharded job is exact (same result as the reference on that file)
-    path = gen_dataset(w, seed=1, stream=rank)
+    parity = sharded_parity_check(fb, torch, dist, rank, world, local) if world > 1 else None
+    # One job = N contiguous shards of one read stream, shard g on GPU g; the sharded job is exact (same result as the
+    # reference on the concatenated file).  weak: every shard is a full-size read sample of the workload's genome (N x
+    # the coverage in total).  strong: the workload's reads are split into N shards (total work fixed).
+    pairs = None
+    if args.scaling == "strong" and world > 1:
+        pairs = int(w["genome"] * w["cov"] / (2.0 * w["length"])) // world
+    path = gen_dataset(w, seed=1, stream=rank, pairs=pairs, tag=f"_s{world}" if pairs else "")
     raw = np.fromfile(path, dtype=np.uint8)
     n_text = raw.size
     reads = int(np.count_nonzero(raw == 10)) // 4
@@ -277,14 +366,15 @@ def run_ours(args, w):
     barrier()
     clk = clocks.stop()
     launches = sess.launches - launches0
-    kernel_ms = {name: sess.kernel_ms(name) for name in ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry", "stitch_verify", "stitch_flow_prep")}
+    kernel_ms = {name: sess.kernel_ms(name) for name in KERNELS}
     sess.set_profiling(False)
     lstats = sess.load_stats()
     stitch_info, n_junc = {}, 0
     if rank == 0:
-        recs, _ = sess.junctions()  # gathers the map once (not timed); publishes the stitch round counters
+        recs, _ = sess.junctions()  # gathers the map once (not timed); publishes the stitch counters
         n_junc = len(recs)
-        stitch_info = {k_: v for k_, v in fb.timings().items() if k_.startswith(("stitch_", "epoch", "exact_", "dry_", "nonquiet", "writer"))}
+        stitch_info = {k_: v for k_, v in fb.timings().items()
+                       if k_.startswith(("stitch_r", "stitch_d", "epoch", "exact_", "dry_", "nonquiet", "writer"))}
     b2, _ = sess.get_bloom_full() if world > 1 else sess.get_bloom()
     weight2 = float(np.unpackbits(b2).sum()) / (1 << lt)
 
@@ -292,7 +382,8 @@ def run_ours(args, w):
     hptr = (host.data_ptr(), n_text)
     two_uploads = False
     bloo2 = np.empty((1 << lt) // 8, np.uint8)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps
+    extra = {}
     if world == 1:
         e2e_parts = [0.0, 0.0]
         # One upload for both passes: pass 1 leaves the parsed planes of the stream in HBM ("retain_planes") and
@@ -329,6 +420,33 @@ def run_ours(args, w):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert n_junc_e2e == n_junc, (n_junc_e2e, n_junc)
+    if world == 1 and not os.environ.get("FAUCET_BENCH_SKIP_EXTRAS"):
+        # (a) the drop-in entry points proper: reads FILE (page-cache warm) -> outputs on the host
+        fsteps = max(1, min(args.steps, 5))
+
+        def step_file():
+            fb.load_two_filters(path, True, k, lt, nh, out=bloo2)
+            return len(fb.scan_retained(True, True, k, J, MAX_SPACER, None, lt, nh)[0])
+        step_file()
+        t0 = time.perf_counter()
+        for _ in range(fsteps):
+            nf = step_file()
+        ef = (time.perf_counter() - t0) / fsteps
+        assert nf == n_junc
+        extra["e2e_file"] = {"value": kmers_per_pass / ef, "unit": "k-mers/s", "steps": fsteps,
+                             "api": "faucet_gpu_load_two_filters(path) + faucet_gpu_scan_retained",
+                             "h2d_bytes_per_step": n_text, "d2h_bytes_per_step": bloo2.nbytes + 32 * int(n_junc)}
+        # (b) once with graph cleaning's inputs: both pair filters (the long one is replayed on the host)
+        sl, snh = fb.geometry_optimal(w["est"] // 20, 0.01)
+        ll, lnh = fb.geometry_optimal(w["est"] // 10, 0.01)
+        spf, lpf = np.zeros((1 << sl) // 8, np.uint8), np.zeros((1 << ll) // 8, np.uint8)
+        t0 = time.perf_counter()
+        fb.load_two_filters_mem(hptr, True, k, lt, nh, out=bloo2)
+        rc_, _ = fb.scan_retained(True, False, k, J, MAX_SPACER, None, lt, nh, spf, (sl, snh), lpf, (ll, lnh))
+        ec = time.perf_counter() - t0
+        extra["e2e_cleaning"] = {"value": kmers_per_pass / ec, "unit": "k-mers/s", "steps": 1,
+                                 "api": "..._mem + faucet_gpu_scan_retained(no_cleaning=0, short + long pair filters)",
+                                 "junctions": len(rc_)}
     if job is not None:
         barrier()
         sess.close_peers()
@@ -346,21 +464,21 @@ def run_ours(args, w):
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         r_contained = 1.0 - (lstats.fresh_kmers / lstats.kmers if lstats.kmers else 0.0)
-        a_load, a_scan = algorithmic_bytes(w, nh, weight2, r_contained)
-        dom = max(("load_A", "scan_flags"), key=lambda n: kernel_ms[n][0])
-        per_launch_ms = kernel_ms[dom][0] / max(1, kernel_ms[dom][1])
-        a_dom = a_scan if dom == "scan_flags" else a_load
-        achieved = kmers_per_pass * a_dom / (per_launch_ms * 1e-3) / 1e9
+        a_load, a_scan = survey_bytes(w, nh, weight2, r_contained)
         text_per_kmer = n_text / max(1, kmers_per_pass)
-        own_bytes = (8.0 + text_per_kmer * (0.375 + 1.0)) if dom == "scan_flags" else a_dom
+        per_step = {n: v[0] / args.steps for n, v in kernel_ms.items()}
+        model = kernel_bytes(w, nh, weight2, r_contained, text_per_kmer)
+        dom = max(per_step, key=lambda n: per_step[n])        # the kernel with the most time per step
+        achieved = kmers_per_pass * model[dom] / (per_step[dom] * 1e-3) / 1e9
+        value = kmers_all * args.steps / (ms_all * 1e-3)
         out = {
-            "metric": "k-mers/sec (Bloom load + junction scan)", "value": kmers_all * args.steps / (ms_all * 1e-3),
+            "metric": METRIC, "value": value,
             "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": w["desc"], "k": k, "log2_tai": lt, "n_hash": nh, "j": J,
-                       "max_spacer_dist": MAX_SPACER, "reads_per_gpu": reads, "kmers_per_pass_per_gpu": kmers_per_pass,
-                       "text_bytes_per_gpu": n_text, "junctions": int(n_junc), "resident_batches": len(parts),
+            "config": config_of(w, k, lt, nh),
+            "detail": {"reads_per_gpu": reads, "kmers_per_pass_per_gpu": kmers_per_pass, "text_bytes_per_gpu": n_text,
+                       "junctions": int(n_junc), "resident_batches": len(parts),
                        "l2": "inputs (%.0f MB text + planes) exceed the 126 MB L2" % (n_text / 1e6),
                        "parallelism": ("%d contiguous shards of one read stream (one per GPU): exact P2P prefix-OR / OR all-reduce "
                                        "of the Bloom filters over NVLink, junction stitch on GPU 0" % world) if world > 1 else "single GPU"},
@@ -371,22 +489,27 @@ def run_ours(args, w):
                     "d2h_bytes_per_step": bloo2.nbytes + 32 * int(n_junc), "steps": e2e_steps,
                     **({"load_call_ms": 1e3 * e2e_parts[0] / e2e_steps, "scan_call_ms": 1e3 * e2e_parts[1] / e2e_steps}
                        if world == 1 else {})},
+            **extra,
             "gpu_launches": int(launches),
             "clocks": clk,
+            # the kernel with the largest share of the step, against ITS OWN byte model (kernel_bytes): algorithmic bytes per
+            # step / that kernel's CUDA-event time per step.  `traffic` = ncu DRAM bytes of that kernel per step.
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom), "peak_kind": peak_kind,
-                         "bytes_per_kmer": a_dom, "launch_ms": per_launch_ms,
-                         # SURVEY 8(d)'s sector model = the bytes the REFERENCE's algorithm moves per k-mer.  The memoised
-                         # scan_flags looks the 16 result bits of a k-mer up instead of re-deriving them, so it moves far
-                         # fewer (`traffic`): frac > 1 means work avoided, not bandwidth exceeded.  `own_*`: what this
-                         # kernel itself has to move (8-byte memo word + planes in + flags out per k-mer start).
-                         "own_bytes_per_kmer": own_bytes, "own_achieved": kmers_per_pass * own_bytes / (per_launch_ms * 1e-3) / 1e9,
-                         "own_frac": kmers_per_pass * own_bytes / (per_launch_ms * 1e-3) / 1e9 / peak},
-            "kernels_ms_per_step": {n: v[0] / args.steps for n, v in kernel_ms.items()},
+                         "bytes_per_kmer": model[dom], "ms_per_step": per_step[dom], "share_of_step": per_step[dom] / (ms_all / args.steps),
+                         # every kernel the same way, and SURVEY 8(d)'s whole-path figure (the bytes the REFERENCE's algorithm
+                         # would move per k-mer, A_load + A_scan, at this k-mer rate per GPU)
+                         "per_kernel_frac": {n: (kmers_per_pass * model[n] / (per_step[n] * 1e-3) / 1e9 / peak) if per_step[n] > 0 else None
+                                             for n in per_step},
+                         "survey_bytes_per_kmer": a_load + a_scan,
+                         "survey_path_frac": (value / world) * (a_load + a_scan) / 1e9 / peak},
+            "kernels_ms_per_step": per_step,
             "bloom_weight2": weight2, "contained_fraction": r_contained, "stitch": stitch_info,
         }
+        if parity is not None:
+            out["parity_check"] = parity
         if args.cpu_baseline:
-            kind, ck, times, sample = cpu_reference_sample(w, k, lt, nh, path, int(os.environ.get("FAUCET_REF_SAMPLE_READS", "60000")))
+            kind, ck, times, sample = cpu_reference_sample(w, lt, nh)
             out["cpu_baseline"] = {"value": ck / times[0], "unit": "k-mers/s", "cores": 1, "kind": kind, "sample": sample}
         print(json.dumps(out))
     if world > 1:
@@ -400,6 +523,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one full-size read sample per GPU; strong = the workload's reads split over the GPUs")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("FAUCET_BENCH_PROFILE_RUN"):

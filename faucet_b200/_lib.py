@@ -74,6 +74,7 @@ def _load():
     L.faucet_gpu_scan_mem.argtypes = [C.c_void_p, C.c_size_t] + scan_tail
     L.faucet_gpu_scan_retained.argtypes = scan_tail[1:]  # no text and no fastq flag: the retained planes know
     L.faucet_gpu_free.argtypes = [C.c_void_p]
+    L.faucet_gpu_query_ext_masks.argtypes = [_u64p, C.c_uint64, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _u8p]
     L.faucet_gpu_set_batch_bytes.argtypes = [C.c_size_t]
     L.faucet_gpu_set_epoch_limit.argtypes = [C.c_uint64]
     L.faucet_gpu_set_tuning.argtypes = [C.c_char_p, C.c_uint64]
@@ -198,14 +199,23 @@ def load_two_filters_mem(text, fastq, k, log2_tai, n_hash, want_bloo1=False, out
     return b2, b1, st
 
 
-def load_two_filters(path, fastq, k, log2_tai, n_hash, want_bloo1=False):
+def load_two_filters(path, fastq, k, log2_tai, n_hash, want_bloo1=False, out=None):
     nb = (1 << log2_tai) // 8
-    b2 = np.empty(nb, np.uint8)
+    b2 = np.empty(nb, np.uint8) if out is None else out
     b1 = np.empty(nb, np.uint8) if want_bloo1 else None
     st = LoadStats()
     _check(lib.faucet_gpu_load_two_filters(path.encode(), int(fastq), k, log2_tai, n_hash, _ptr(b2), _ptr(b1),
                                            C.byref(st)))
     return b2, b1, st
+
+
+def query_ext_masks(kmers, k, j, bloo2, log2_tai, n_hash):
+    """batched getValidJExtension queries: u8 per k-mer, low nibble = Bloom members among the 4 forward extensions,
+    high nibble = those that also pass the depth-j check"""
+    km = np.ascontiguousarray(np.asarray(kmers, np.uint64))
+    out = np.zeros(len(km), np.uint8)
+    _check(lib.faucet_gpu_query_ext_masks(km.ctypes.data_as(_u64p), len(km), k, j, _ptr(bloo2), log2_tai, n_hash, _ptr(out)))
+    return out
 
 
 def _take_recs(recs, n):

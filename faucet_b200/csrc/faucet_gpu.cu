@@ -37,9 +37,10 @@ struct Global {
   int res_log2 = 24;                           // reservation table entries (u32 each)
   uint32_t stitch_w_max = 1u << 15, stitch_w0 = 2048, stitch_shrink_den = 4, stitch_grow_den = 10;
   int stitch_blocks = 3;  // resident stitch CTAs per SM the kernel is compiled for (2, 3 or 4)
-  // epochs of the stitch (stitch.cuh): 0 = one ordered run per batch, 1 = adaptive (ordered while most records write,
-  // then classify / execute / verify / apply), 2 = classify from the first record on (tests)
-  int epoch_mode = 1;
+  // epochs of the stitch (stitch.cuh): 0 = every record through the ordered executor (the default: with the dataflow
+  // executor it is the fastest on every BASELINE config), 1 = adaptive (ordered while most records write, then
+  // classify / execute / verify / apply), 2 = classify from the first record on (tests)
+  int epoch_mode = 0;
   uint32_t epoch0 = 8192, epoch_max = 1u << 20;  // first / largest epoch, records
   uint32_t epoch_switch_pct = 30;                // an ordered epoch with fewer writers than this switches to classify epochs
   uint32_t epoch_shrink_pct = 14, epoch_grow_pct = 6;  // exact-set share above / below which the epoch halves / doubles
@@ -948,7 +949,7 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->flow_fn, STITCH_THREADS, smem));
     if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_flow_kernel cannot be made resident");
     s->flow_grid = per_sm * g.sm_count;
-    if ((rc = dmalloc(&s->d_fbig, 1))) return rc;
+    if ((rc = dmalloc(&s->d_fbig, 64))) return rc;  // [0] = long-line count, [32] = the ticket counter (its own 128-byte line)
   }
   const int grid = g.sm_count * 8;
   for (uint32_t b0 = begin; b0 < end;) {
@@ -969,7 +970,7 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
     a.dirty = mark_dirty ? s->d_dirty : nullptr; a.dirty_max = mark_dirty ? s->d_dirty_max : nullptr;
     FlowArgs f;
     std::memset(&f, 0, sizeof f);
-    f.n = n; f.begin = b0; f.rows = s->d_frows; f.preds = s->d_fpreds; f.done = s->d_fdone; f.counts = s->d_fcounts; f.big = s->d_fbig;
+    f.n = n; f.begin = b0; f.rows = s->d_frows; f.preds = s->d_fpreds; f.done = s->d_fdone; f.counts = s->d_fcounts; f.big = s->d_fbig; f.next = s->d_fbig + 32;
     uint32_t tail[2] = {0, 0};  // last count and its prefix: their sum is the number of pairs
     unsigned int big = 0;
     {
@@ -1027,6 +1028,7 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
     while (true) {
       struct { unsigned int next, nd[2], W, round, status; } z = {0, {0, 0}, s->h_st.W, s->h_st.round, ST_DONE};
       CU(cudaMemcpyAsync(&s->d_st->next, &z, sizeof z, cudaMemcpyHostToDevice, s->stream));
+      CU(cudaMemsetAsync(s->d_fbig + 32, 0, 4, s->stream));
       void* params[] = {&a, &f};
       {
         KTimer kt(s, KT_STITCH);
@@ -1838,6 +1840,39 @@ int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int
   drain_events(s);
   if (trace) fprintf(stderr, "scan_retained: collect %.2f ms\n", now() - t_collect);
   return rc;
+}
+
+// Batched Bloom walks for the contig build: see ext_masks_kernel (scan.cuh).
+int faucet_gpu_query_ext_masks(const uint64_t* kmers, uint64_t n, int k, int j, const uint8_t* bloo2, int log2_tai, int n_hash,
+                               uint8_t* masks_out) {
+  if (j < 0 || j > MAX_J) return fail(FAUCET_E_ARG, "j must be in [0,4]");
+  if (n && (!kmers || !masks_out)) return fail(FAUCET_E_ARG, "NULL array");
+  faucet_session* s = nullptr;
+  int rc = get_session(&s, k, log2_tai, n_hash, j, 0);
+  if (rc) return rc;
+  if (bloo2) { if ((rc = faucet_session_set_bloom(s, bloo2))) return rc; }  // NULL: the device copy the last pass left behind
+  else if (!s->d_bloom) return fail(FAUCET_E_STATE, "no bloo2 on the device: pass the filter");
+  if (!n) return 0;
+  unsigned long long* d_k = nullptr;
+  uint8_t* d_m = nullptr;
+  if ((rc = dmalloc(&d_k, n)) || (rc = dmalloc(&d_m, n))) { cudaFree(d_k); return rc; }
+  ScanArgs a{};
+  a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = k; a.j = j; a.n_hash = n_hash;
+  cudaMemcpyAsync(d_k, kmers, n * 8, cudaMemcpyHostToDevice, s->stream);
+  const int grid = (int)std::min<uint64_t>((uint64_t)g.sm_count * 8, (n + 255) / 256);
+  switch (n_hash) {
+    case 1: ext_masks_kernel<1><<<grid, 256, 0, s->stream>>>(a, d_k, n, d_m); break;
+    case 2: ext_masks_kernel<2><<<grid, 256, 0, s->stream>>>(a, d_k, n, d_m); break;
+    case 3: ext_masks_kernel<3><<<grid, 256, 0, s->stream>>>(a, d_k, n, d_m); break;
+    case 4: ext_masks_kernel<4><<<grid, 256, 0, s->stream>>>(a, d_k, n, d_m); break;
+    default: ext_masks_kernel<0><<<grid, 256, 0, s->stream>>>(a, d_k, n, d_m); break;
+  }
+  s->launches++;
+  cudaMemcpyAsync(masks_out, d_m, n, cudaMemcpyDeviceToHost, s->stream);
+  cudaError_t e = cudaStreamSynchronize(s->stream);
+  cudaFree(d_k); cudaFree(d_m);
+  if (e != cudaSuccess) return fail(FAUCET_E_CUDA, std::string("ext_masks: ") + cudaGetErrorString(e));
+  return check_launch("ext_masks");
 }
 
 // The path forms stream the file: a reader thread, pinned staging buffers, O(batch) host memory.  The session

@@ -22,7 +22,7 @@ namespace faucet {
 #define FAUCET_FLOW_BLOCKS 3
 #endif
 #ifndef FAUCET_FLOW_SLEEP
-#define FAUCET_FLOW_SLEEP 200
+#define FAUCET_FLOW_SLEEP 100
 #endif
 constexpr uint32_t PRED_NONE = 0xffffffffu;
 constexpr int RADIX_SUB = 512;      // pairs per warp of the radix passes (16 steps of 32, in order: stable)
@@ -43,7 +43,21 @@ struct FlowArgs {
   uint32_t n_pairs;
   int shift;
   unsigned int* big;          // records with more slots than a row holds (they need the round-based kernel)
+  unsigned int* next;         // the ticket counter, alone in its cache line (every warp of the grid hammers it)
 };
+// Tickets.  One global counter hit by every warp for every record is a same-address atomic per record (~6 ns each,
+// serialised at one L2 slice: it alone capped the executor at ~160 M records/s); a warp that takes SEVERAL tickets at
+// once sits on records it has not started, and everything that depends on them waits (4 per warp: 1.8x slower, 16:
+// 17x).  So each CTA draws FAUCET_FLOW_POOL tickets at a time into a shared-memory pool and its warps take them one by
+// one: the global atomics drop by that factor and a drawn ticket is picked up within a fraction of a record time.
+// The jslot run filter (stitch.cuh, prefetch_line) halves the executor's L2 sectors but puts one more dependent load in
+// front of the key probes; the executor is bound by the latency of a record (its dependents wait for it), not by sectors.
+#ifndef FAUCET_FLOW_JSLOT
+#define FAUCET_FLOW_JSLOT 0
+#endif
+#ifndef FAUCET_FLOW_POOL
+#define FAUCET_FLOW_POOL 8
+#endif
 
 __global__ void __launch_bounds__(DRY_THREADS) flow_rows_kernel(StitchArgs a, FlowArgs f) {
   __shared__ uint32_t keep_s[DRY_WARPS][ROW_WORDS];
@@ -51,6 +65,7 @@ __global__ void __launch_bounds__(DRY_THREADS) flow_rows_kernel(StitchArgs a, Fl
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * DRY_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * DRY_THREADS) >> 5;
   for (uint32_t i = gw; i < f.n; i += n_warps) {
+    const unsigned long long t_take = gtime_ns();
     const uint32_t rec = a.list ? __ldg(a.list + i) : f.begin + i;
     const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
     const uint32_t len = le > ls ? le - ls : 0u;
@@ -150,16 +165,21 @@ __global__ void flow_preds_kernel(FlowArgs f) {
   }
 }
 
+// The done flags are polled with an L2 (ld.cg) load.  An acquire -- or even relaxed -- gpu-scope load is followed by an invalidation of the
+// SM's whole L1 (CCTL.IVALL in SASS), per poll, for every warp of the SM -- and nothing here needs it: what a record reads
+// after the wait and another record may have written (keys, records, stamps, jslot) is read with ld.cg, i.e. from L2,
+// where the writer's atomics and its release store were performed in order; the loads are issued after the branch on
+// the flag value (no speculation), and what IS cached in L1 (text planes, flags, rows) is never written by this kernel.
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// The persistent executor.  st->next = next list entry to hand out; entries already flagged done (a relaunch after
+// The persistent executor.  *f.next = next list entry to hand out; entries already flagged done (a relaunch after
 // the table grew or the extension buffer was drained) are skipped.
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_flow_kernel(StitchArgs a, FlowArgs f) {
@@ -173,12 +193,28 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_flow_kernel
   __syncwarp();
   c.S = S; c.stage = S->stage; c.cnt = S->st; c.n_stage = 0; c.part = 0; c.stamp = 0; c.n_vis = 0; c.wrote = false;
   c.land_slot = nullptr; c.land_nt = nullptr; c.n_land = 0; c.emit = true;
+  __shared__ unsigned long long pool;  // {end : 32 | next : 32} of the CTA's drawn tickets
+  if (threadIdx.x == 0) pool = 0ull;
+  __syncthreads();
   while (true) {
     uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(&st->next, 1u);
+    if (lane == 0) {
+      while (true) {
+        const unsigned long long v = atomicAdd(&pool, 1ull);  // optimistic: take the next ticket of the pool
+        const uint32_t nx = (uint32_t)v, en = (uint32_t)(v >> 32);
+        if (nx < en) { i = nx; break; }
+        if (nx == en) {  // this warp found the pool just empty: it draws the next batch and keeps its first ticket
+          i = atomicAdd(f.next, (unsigned int)FAUCET_FLOW_POOL);
+          atomicExch(&pool, ((unsigned long long)(i + FAUCET_FLOW_POOL) << 32) | (unsigned long long)(i + 1u));
+          break;
+        }
+        while ((uint32_t)(*(volatile unsigned long long*)&pool >> 32) == en) {}  // somebody is drawing: retry after
+      }
+    }
     i = __shfl_sync(0xffffffffu, i, 0);
     if (i >= f.n) break;
     if (ld_acquire_u32(f.done + i)) continue;
+    const unsigned long long t_take = gtime_ns();
     const uint32_t rec = a.list ? __ldg(a.list + i) : f.begin + i;
     const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
     const uint32_t len = le > ls ? le - ls : 0u;
@@ -193,32 +229,43 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_flow_kernel
     const uint32_t* pr = f.preds + (size_t)i * ROW_WORDS;
     const uint32_t n_row = __ldg(f.rows + (size_t)i * ROW_WORDS);
     const uint32_t pred = lane < (int)n_row ? __ldg(pr + 1 + lane) : PRED_NONE;
-    if (lane == 0 && 2ull * len + 2 > __ldcg(&st->max_need)) atomicMax(&st->max_need, 2ull * len + 2);
+    // ---- room for what this record and the other resident warps may create?  (Read before the wait: the bound covers
+    // every record in flight, so what the predecessors create meanwhile is already counted.)
+    unsigned int stop = ST_DONE;
+    {
+      unsigned long long need = __ldcg(&st->max_need);
+      if (2ull * len + 2 > need) { need = 2ull * len + 2; if (lane == 0) atomicMax(&st->max_need, need); }
+      const unsigned long long bound = need * n_warps;
+      if (__ldcg(&st->n_entries) + bound > a.cap / 2) stop = ST_GROW_TABLE;
+      else if (a.ext && __ldcg(&st->ext_used) + 2 * bound + n_warps > a.ext_cap) stop = ST_DRAIN_EXT;
+    }
     // ---- wait for the earlier records that share a slot with this one (or for the run to be called off)
     bool off = false;
+    const unsigned long long t_wait = gtime_ns();
+    uint32_t polls = 0;
     while (true) {
       const bool ready = pred == PRED_NONE || ld_acquire_u32(f.done + pred) != 0u;
       if (__all_sync(0xffffffffu, ready)) break;
       if (__ldcg(&st->status) != ST_DONE) { off = true; break; }
+      polls++;
       __nanosleep(FAUCET_FLOW_SLEEP);
     }
-    if (off) continue;  // (keeps taking entries: they all see the status and fall through)
-    // ---- room for what this record and the other resident warps may create?
-    {
-      const unsigned long long bound = __ldcg(&st->max_need) * n_warps;
-      unsigned int stop = ST_DONE;
-      if (__ldcg(&st->n_entries) + bound > a.cap / 2) stop = ST_GROW_TABLE;
-      else if (a.ext && __ldcg(&st->ext_used) + 2 * bound + n_warps > a.ext_cap) stop = ST_DRAIN_EXT;
-      if (stop != ST_DONE) { if (lane == 0) atomicCAS(&st->status, (unsigned int)ST_DONE, stop); continue; }
-      if (__ldcg(&st->status) != ST_DONE) continue;
+    const unsigned long long t_go = gtime_ns();
+    if (lane == 0) {  // executor statistics (reported as faucet_timings.stitch_phase_ns[0..5])
+      S->st[SS_T_PHASE1] += polls; S->st[SS_T_SYNC1] += polls ? 1 : 0; S->st[SS_T_PHASE2] += t_go - t_wait;
+      S->st[SS_T_P1A] += t_wait - t_take;
     }
+    if (off) continue;  // (keeps taking entries: they all see the status and fall through)
+    if (stop != ST_DONE) { if (lane == 0) atomicCAS(&st->status, (unsigned int)ST_DONE, stop); continue; }
+    if (__ldcg(&st->status) != ST_DONE) continue;
     __syncwarp();
     c.rec = rec; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls; c.wrote = false;
     c.stamp = (a.rec_base + rec) << STAMP_SHIFT;
     if (fast) {
       if (lane < (int)n_row) S->reskey[lane] = __ldg(f.rows + (size_t)i * ROW_WORDS + 1 + lane);
       __syncwarp();
-      prefetch_line<2>(a, S, ls, n_pos, lane, (int)n_row);
+      prefetch_line<2>(a, S, ls, n_pos, lane, FAUCET_FLOW_JSLOT ? (int)n_row : -1);
+      if (lane == 0) S->st[SS_T_P1C] += gtime_ns() - t_go;
       c.n_pos = n_pos; c.pk = S->pk; c.pk_base = ls & ~15u; c.inv = S->inv; c.inv_base = ls & ~31u;
       scan_line<true, false>(a, c, ls, ls + len, lane);
     } else if (len) {
@@ -227,9 +274,14 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_flow_kernel
     }
     if (a.ext && c.n_stage) ext_flush(a, c, lane);
     if (c.wrote && lane == 0) S->st[SS_WRITERS]++;
+    if (lane == 0) S->st[SS_T_P2A] += gtime_ns() - t_go;
+    // every write a later record may read (keys, stamps, records, jslot / dirty marks) was issued by lane 0: its release
+    // store orders them before the flag
     __syncwarp();
-    __threadfence();
-    if (lane == 0) st_release_u32(f.done + i, 1u);
+    if (lane == 0) {
+      st_release_u32(f.done + i, 1u);
+      S->st[SS_T_SYNC2] += gtime_ns() - t_go; S->st[SS_T_P1B] += 1;
+    }
   }
   __syncwarp();
   if (lane < SS_COUNT && S->st[lane]) atomicAdd(&st->stats[lane], S->st[lane]);

@@ -498,4 +498,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
   }
 }
 
+// Batched form of JunctionMap::getValidJExtension (utils/JunctionMap.cpp:474-490), the Bloom query the contig build
+// repeats at every step of findNeighbor (:231-462): for each oriented k-mer, which of its four forward extensions are
+// Bloom members (low nibble) and which of those pass the depth-j check (high nibble).
+template <int NH>
+__global__ void ext_masks_kernel(ScanArgs a, const unsigned long long* __restrict__ kmers, unsigned long long n,
+                                 uint8_t* __restrict__ out) {
+  const uint64_t mask = kmer_mask(a.k);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t x = kmers[i] & mask, xrc = revcomp(x, a.k);
+    uint32_t m = 0;
+    for (uint32_t nt = 0; nt < 4; nt++) {
+      const uint64_t y = ext_fwd(x, nt, mask), yrc = ext_rc(xrc, nt, a.k);
+      if (bloom_contains<NH>(a, y, yrc)) {
+        m |= 1u << nt;
+        if (jcheck<NH>(a, y, yrc, mask)) m |= 16u << nt;
+      }
+    }
+    out[i] = (uint8_t)m;
+  }
+}
+
 }  // namespace faucet

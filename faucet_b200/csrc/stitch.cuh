@@ -493,6 +493,15 @@ __device__ __forceinline__ uint32_t landing_updates(const StitchArgs& a, int slo
   return wr;
 }
 
+// What the walk knows about a junction's record without asking memory again: dist[fwdIdx], dist[backIdx] and the link
+// mask as parked by prefetch_line (or zeros for a junction this line just created).  The keys of a running record are
+// private to it, so these stay true until the line itself changes them -- which it tracks -- and the updates of a
+// landing can be issued as fire-and-forget reductions, only where they change something.
+struct KnownRec {
+  uint32_t d_fwd, d_back, link;
+  bool ok;  // false: the line touched this junction before (the parked values may be stale): ask memory
+};
+
 // scan_forward (src/ReadScanner.cpp:112-231) on the valid sub-read at byte offset s0, `len` bases.
 // FAST: the line's lookups were parked in shared memory in phase 1 (c.S, index = s0 - c.ls + pos).
 template <bool FAST>
@@ -505,6 +514,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
   bool have_last = false;
   int last_tp = 0, last_fwd_idx = 0, last_slot = -1;
   uint64_t last_key = 0;
+  KnownRec last_rec = {0, 0, 0, false};
   OutList o;
   const bool pairs = !a.no_cleaning && a.spf != nullptr;
   const bool want_ext = a.ext != nullptr;
@@ -574,61 +584,93 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       if (FAST) line_publish(a, c, key, slot, lane);
     }
     const bool seen = line_visited(c, slot, lane);
+    KnownRec cur = {0, 0, 0, false};
+    if (created) cur.ok = true;  // a zeroed record
+    else if (FAST && known && !seen) {
+      const int hs = 2 * (rel + pos) + dir;
+      cur.d_fwd = c.S->hop[hs]; cur.d_back = c.S->dback[hs]; cur.link = c.S->lnk[hs]; cur.ok = true;
+    }
     uint32_t wr = 0;
-    if (lane == 0) wr = landing_updates(a, slot, real, back_idx, created, have_last, last_slot, last_fwd_idx, tp - last_tp, tp - 2 * j);
     int dist;
-    if (created) dist = 0;  // a zeroed record; back_idx != fwd_idx, so nothing written above shows here
-    else if (FAST && known && !seen) dist = c.S->hop[2 * (rel + pos) + dir];
-    else {
-      dist = lane == 0 ? (int)rec_dist_now(a, slot, fwd_idx) : 0;
-      dist = __shfl_sync(0xffffffffu, dist, 0);
+    if (cur.ok && (!have_last || last_rec.ok)) {
+      // every value is known: reductions only where something changes (warp-uniform decisions, lane 0 issues)
+      wr = created ? 5u : 0u;
+      if (lane == 0) rec_add_cov(a, slot, real);
+      if (have_last) {  // directLinkJunctions (utils/JunctionMap.cpp:551-561)
+        const uint32_t dv = (uint32_t)(tp - last_tp) & 0xffu;
+        if (dv > last_rec.d_fwd) { wr |= 6u; if (lane == 0) rec_update(a, last_slot, last_fwd_idx, (int)dv); }
+        if (!((last_rec.link >> last_fwd_idx) & 1u)) { wr |= 4u; if (lane == 0) rec_link(a, last_slot, last_fwd_idx); }
+        if (dv > cur.d_back) { wr |= 5u; cur.d_back = dv; if (lane == 0) rec_update(a, slot, back_idx, (int)dv); }
+        if (!((cur.link >> back_idx) & 1u)) { wr |= 4u; cur.link |= 1u << back_idx; if (lane == 0) rec_link(a, slot, back_idx); }
+      } else {
+        const uint32_t dv = (uint32_t)(tp - 2 * j) & 0xffu;
+        if (dv > cur.d_back) { wr |= 5u; cur.d_back = dv; if (lane == 0) rec_update(a, slot, back_idx, (int)dv); }
+      }
+      dist = (int)cur.d_fwd;
+    } else {
+      if (lane == 0) wr = landing_updates(a, slot, real, back_idx, created, have_last, last_slot, last_fwd_idx, tp - last_tp, tp - 2 * j);
+      wr = __shfl_sync(0xffffffffu, wr, 0);
+      if (created) dist = 0;  // a zeroed record; back_idx != fwd_idx, so nothing written above shows here
+      else {
+        dist = lane == 0 ? (int)rec_dist_now(a, slot, fwd_idx) : 0;
+        dist = __shfl_sync(0xffffffffu, dist, 0);
+      }
+      cur.ok = false;
     }
     if (dist < 1) dist = 1;
     if (lane == 0) { c.cnt[SS_PROCESSED] += 1; c.cnt[SS_SKIPPED] += (unsigned long long)(dist - 1); }
     line_visit(c, slot, lane);
-    wr = __shfl_sync(0xffffffffu, wr, 0);
     if (wr) {
       c.wrote = true;
       mark_written(a, key, c.rec, created, (wr & 1u) != 0, lane);
       mark_written(a, last_key, c.rec, false, (wr & 2u) != 0, lane);
     }
-    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
+    if (pairs || want_ext) out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
     have_last = true;
-    last_junc_pos = tp; last_tp = tp; last_slot = slot; last_fwd_idx = fwd_idx; last_key = key;
+    last_junc_pos = tp; last_tp = tp; last_slot = slot; last_fwd_idx = fwd_idx; last_key = key; last_rec = cur;
     tp += dist;
   }
   if (!have_last) {  // add_fake_junction (:92-104): mid-read, facing forward
     const int pos = len / 2 - k / 2;
     const uint64_t key = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
     const int real = (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base);
-    int slot = 0;
+    const int mtp = 2 * pos + 1;
+    const uint32_t d4 = (uint32_t)(mtp - 2 * j) & 0xffu, dr = (uint32_t)((2 * len - mtp - 2 * k + 1) - 2 * j) & 0xffu;
+    int slot = FAST ? c.S->slot[2 * (rel + pos) + 1] : -1;
     bool created = false;
     uint32_t wr = 0;
-    if (lane == 0) {
-      c.cnt[SS_NOJUNC]++;
-      slot = tbl_insert(a, key, &created);
-      if (created) { a.stamps[slot] = c.stamp++; wr = 1u; }
-      rec_add_cov(a, slot, real);
-      const int mtp = 2 * pos + 1;
-      const uint32_t d4 = (uint32_t)(mtp - 2 * j) & 0xffu, dr = (uint32_t)((2 * len - mtp - 2 * k + 1) - 2 * j) & 0xffu;
-      if (atomicMax(rec_field(a, slot, REC_DIST + 4), d4) < d4) wr = 1u;
-      if (atomicMax(rec_field(a, slot, REC_DIST + real), dr) < dr) wr = 1u;
+    if (lane == 0) c.cnt[SS_NOJUNC]++;
+    if (FAST && slot >= 0 && !line_visited(c, slot, lane)) {  // it is there already: its parked distances say what changes
+      const int hs = 2 * (rel + pos) + 1;
+      if (lane == 0) rec_add_cov(a, slot, real);
+      if (d4 > c.S->dback[hs]) { wr = 1u; if (lane == 0) rec_update(a, slot, 4, (int)d4); }
+      if (dr > c.S->hop[hs]) { wr = 1u; if (lane == 0) rec_update(a, slot, real, (int)dr); }
+    } else {
+      if (lane == 0) {
+        slot = tbl_insert(a, key, &created);
+        if (created) { a.stamps[slot] = c.stamp++; wr = 1u; }
+        rec_add_cov(a, slot, real);
+        if (atomicMax(rec_field(a, slot, REC_DIST + 4), d4) < d4) wr = 1u;
+        if (atomicMax(rec_field(a, slot, REC_DIST + real), dr) < dr) wr = 1u;
+      }
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      created = __shfl_sync(0xffffffffu, (int)created, 0) != 0;
+      c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
+      wr = __shfl_sync(0xffffffffu, wr, 0);
     }
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    created = __shfl_sync(0xffffffffu, (int)created, 0) != 0;
-    c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
-    wr = __shfl_sync(0xffffffffu, wr, 0);
     if (wr) { c.wrote = true; mark_written(a, key, c.rec, created, true, lane); }
     if (FAST && created) line_publish(a, c, key, slot, lane);
     line_visit(c, slot, lane);
-    out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
+    if (pairs || want_ext) out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
   } else {  // :205
+    const uint32_t dv = (uint32_t)((2 * len - last_tp - 2 * k + 1) - 2 * j) & 0xffu;
     uint32_t wr = 0;
-    if (lane == 0) {
-      const uint32_t dv = (uint32_t)((2 * len - last_tp - 2 * k + 1) - 2 * j) & 0xffu;
-      wr = atomicMax(rec_field(a, last_slot, REC_DIST + last_fwd_idx), dv) < dv;
+    if (last_rec.ok) {
+      if (dv > last_rec.d_fwd) { wr = 1u; if (lane == 0) rec_update(a, last_slot, last_fwd_idx, (int)dv); }
+    } else {
+      if (lane == 0) wr = atomicMax(rec_field(a, last_slot, REC_DIST + last_fwd_idx), dv) < dv;
+      wr = __shfl_sync(0xffffffffu, wr, 0);
     }
-    wr = __shfl_sync(0xffffffffu, wr, 0);
     if (wr) { c.wrote = true; mark_written(a, last_key, c.rec, false, true, lane); }
   }
   __syncwarp();

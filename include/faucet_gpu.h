@@ -119,6 +119,15 @@ int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int
                              faucet_scan_stats* stats);
 void faucet_gpu_free(void* p);
 
+/* ---- downstream of the scan: the Bloom walks of the contig build ----------------
+ * Batched form of JunctionMap::getValidJExtension (utils/JunctionMap.cpp:474-490), which findNeighbor (:231-462) asks
+ * at every step between two junctions: for each oriented k-mer kmers[i], masks_out[i] bit nt (0..3, A C T G) = the
+ * forward extension by nt is in bloo2, bit 4+nt = it also passes the depth-j check.  getValidJExtension's answer is
+ * then: no bit of the high nibble -> -1, exactly one -> its index, more -> -2.  bloo2 = NULL uses the device copy
+ * the last load / scan call left behind. */
+int faucet_gpu_query_ext_masks(const uint64_t* kmers, uint64_t n, int k, int j, const uint8_t* bloo2, int log2_tai,
+                               int n_hash, uint8_t* masks_out);
+
 /* ---- tuning / introspection -------------------------------------------------------------- */
 /* bytes of read text per pipelined device batch (default 256 MiB, ramping up from 32 MiB; tests use tiny values to exercise the
  * multi-batch path) and the timestamp epoch length (default 2^32-2) */
@@ -128,8 +137,9 @@ int faucet_gpu_get_timings(faucet_timings* out);
 /* Knobs (none changes a result; tests use them to force every code path).  Setting one drops the cached session.
  *  stitch:  "stitch_exec" 1 = the ordered part runs as a dataflow (per-slot predecessor lists, no grid barrier; default),
  *           0 = in rounds of windowed reservations; "flow_chunk" records per dependency sort;
- *           "epoch_mode" 1 = adaptive epochs (default: ordered kernel while most records write, then read-only classify /
- *           ordered exact set / verify / apply), 0 = one ordered run per batch, 2 = classify epochs from the first record;
+ *           "epoch_mode" 0 = every record through the ordered executor (default), 1 = adaptive epochs (ordered executor
+ *           while most records write, then read-only classify / ordered exact set / verify / apply), 2 = classify epochs
+ *           from the first record on;
  *           "epoch0" / "epoch_max" first / largest epoch in records; "epoch_switch_pct", "epoch_shrink_pct",
  *           "epoch_grow_pct" the thresholds of the epoch controller; "epoch_recheck" 1 = a record with earlier but no later
  *           writes under its slots is walked again on the live table (default), 0 = it joins the exact set; "table_cap0" initial junction-table slots (power of

@@ -96,6 +96,25 @@ uint64_t ref_old_hash(int log2_tai, uint64_t key, int i) {
   return cache[log2_tai]->oldHash(key, i);
 }
 
+// iteration order of a libstdc++ unordered_map<kmer_type, Junction> after inserting `keys` in the given order
+// (what JunctionMap::writeToFile walks, utils/JunctionMap.cpp:579-596)
+void ref_iteration_order(const uint64_t* keys, uint64_t n, uint64_t* out) {
+  std::unordered_map<kmer_type, Junction> m;
+  for (uint64_t i = 0; i < n; i++) m[keys[i]] = Junction();
+  uint64_t j = 0;
+  for (auto it = m.begin(); it != m.end(); ++it) out[j++] = it->first;
+}
+
+// JunctionMap::getValidJExtension (utils/JunctionMap.cpp:474-490) for each oriented k-mer, over the given bloo2
+void ref_valid_j_extension(const uint64_t* kmers, uint64_t n, int j, const uint8_t* bloo2, int log2_tai, int n_hash, int* out) {
+  Bloom* b = make_bloom(log2_tai, n_hash);
+  memcpy(b->blooma, bloo2, ((size_t)1 << log2_tai) / 8);
+  JChecker* jc = new JChecker(j, b);
+  JunctionMap* jm = new JunctionMap(b, jc, 100);
+  for (uint64_t i = 0; i < n; i++) out[i] = jm->getValidJExtension(DoubleKmer(kmers[i]));
+  delete jm; delete jc; delete b;
+}
+
 uint64_t ref_seed(int i) {
   Bloom* b = make_bloom(10, 4);
   uint64_t s = b->seed_tab[i];

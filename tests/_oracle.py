@@ -189,6 +189,24 @@ class Ref:
     def set_k(self, k):
         self.lib.ref_set_k(k)
 
+    def iteration_order(self, keys):
+        """iteration order of the reference's unordered_map after inserting `keys` in the given order"""
+        k = np.ascontiguousarray(np.asarray(keys, np.uint64))
+        out = np.zeros(len(k), np.uint64)
+        self.lib.ref_iteration_order.argtypes = [_u64p, C.c_uint64, _u64p]
+        self.lib.ref_iteration_order(_ptr(k, _u64p), len(k), _ptr(out, _u64p))
+        return out
+
+    def valid_j_extension(self, kmers, k, j, bloo2, log2_tai, n_hash):
+        """JunctionMap::getValidJExtension for each oriented k-mer"""
+        self.set_k(k)
+        km = np.ascontiguousarray(np.asarray(kmers, np.uint64))
+        out = np.zeros(len(km), np.int32)
+        self.lib.ref_valid_j_extension.argtypes = [_u64p, C.c_uint64, C.c_int, _u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        self.lib.ref_valid_j_extension(_ptr(km, _u64p), len(km), j, _ptr(bloo2), log2_tai, n_hash,
+                                       out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
     def geometry_optimal(self, est, fp):
         a, b, c = C.c_int(), C.c_int(), C.c_uint64()
         self.lib.ref_geometry_optimal(est, fp, C.byref(a), C.byref(b), C.byref(c))

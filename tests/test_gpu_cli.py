@@ -69,12 +69,24 @@ def _run2(exe, reads, prefix, k, max_len, est, sing, extra, timeout=900):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
 
 
+def _fastg_text(path):
+    """the reference names FASTG nodes after heap addresses (NODE_0x55d0..., src/ContigGraph.cpp:1470-1500), which change
+    from run to run of the SAME binary: number them by first appearance before comparing"""
+    import re
+    ids = {}
+    return re.sub(r"NODE_0x[0-9a-f]+", lambda m: "NODE_%d" % ids.setdefault(m.group(0), len(ids)), open(path).read())
+
+
 def _same_files(tmp_path, suffixes, ref):
     for suf in suffixes:
         a, b = str(tmp_path / "ours") + suf, str(tmp_path / "ref") + suf
         assert os.path.exists(b), f"reference wrote no {suf}: {ref.stdout[-500:]} {ref.stderr[-500:]}"
         assert os.path.exists(a), f"no {suf} from the GPU path"
-        assert os.path.getsize(a) > 0 and filecmp.cmp(a, b, shallow=False), f"{suf} differs from the reference's file"
+        assert os.path.getsize(a) > 0
+        if suf.endswith(".fastg"):
+            assert _fastg_text(a) == _fastg_text(b), f"{suf} differs from the reference's file (node addresses normalised)"
+        else:
+            assert filecmp.cmp(a, b, shallow=False), f"{suf} differs from the reference's file"
 
 
 @pytest.mark.parametrize("extra,suffixes", [

@@ -118,3 +118,29 @@ def test_c2_prefix_matches_oracle(fb, oracle, c2):
     assert gsst == osst
     for f in ("kmer", "dist", "cov", "linked"):
         assert np.array_equal(grecs[f], orecs[f]), f
+
+
+@pytest.mark.parametrize("log2_tai,n_hash", [(33, 3), (34, 2)])
+def test_big_filter_prefix_matches_oracle(fb, oracle, log2_tai, n_hash):
+    """BASELINE configs[3] / [4] geometry: 2^33- and 2^34-bit filters (1 and 2 GiB, bit positions beyond 32 bits, the
+    saturated-k-mer cache of pass 1 on by default from 2^29 bits) on the first 40 k reads of a 100 bp stream, both
+    filters and the junction map bit for bit against the oracle"""
+    import bench
+    from _oracle import gen_reads
+    d = os.environ.get("FAUCET_BENCH_TMP", "/tmp/faucet_bench")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "bigfilter_prefix.fq")
+    if not os.path.exists(path):
+        gen_reads(path, genome=2_000_000, cov=2, length=100, insert=300, seed=4, err=0.002)
+    text = open(path, "rb").read()
+    k = 31
+    o1, o2, ost = oracle.load_two_filters(text, True, k, log2_tai, n_hash)
+    g2, g1, gst = fb.load_two_filters_mem(text, True, k, log2_tai, n_hash, want_bloo1=True)
+    assert gst.kmers == ost.kmers
+    assert np.array_equal(g2, o2) and np.array_equal(g1, o1)
+    del g1, o1
+    orecs, osst = oracle.scan(text, True, True, 1, k, bench.J, bench.MAX_SPACER, o2, log2_tai, n_hash)
+    grecs, gsst = fb.scan_mem(text, True, True, 1, k, bench.J, bench.MAX_SPACER, g2, log2_tai, n_hash)
+    assert gsst == osst
+    for f in ("kmer", "dist", "cov", "linked"):
+        assert np.array_equal(grecs[f], orecs[f]), f

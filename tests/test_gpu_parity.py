@@ -42,10 +42,11 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
-EPOCH_DEFAULTS = {"epoch_mode": 1, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 20}
+EPOCH_DEFAULTS = {"epoch_mode": 0, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 20}
 EPOCH_SCHEDULES = {
-    "adaptive": {},                                                     # the default: ordered epochs first, then classify epochs
-    "ordered_only": {"epoch_mode": 0},                                  # one run of the ordered (dataflow) executor per batch
+    "adaptive": {"epoch_mode": 1},                                      # ordered epochs first, then classify epochs
+    "ordered_only": {},                                                 # the default: every record through the dataflow executor
+    "ordered_small_chunks": {"flow_chunk": 333},                        # ... with a dependency sort every 333 records
     "rounds_only": {"epoch_mode": 0, "stitch_exec": 0},                 # ... of the round-based ordered kernel
     "classify_rounds": {"epoch_mode": 2, "epoch0": 300, "epoch_max": 5000, "stitch_exec": 0},
     "flow_small_chunks": {"epoch_mode": 1, "epoch0": 1024, "flow_chunk": 700},  # dependency sort every 700 records
@@ -469,11 +470,41 @@ def test_epochs_report_their_work(fb, oracle, tmp_path_factory):
     _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
     orecs, ost = oracle.scan(text, True, True, 1, k, 1, 100, b2, lt, nh)
     try:
+        fb.set_tuning("epoch_mode", 1)
         fb.set_tuning("epoch0", 1024)
         grecs, gst = fb.scan_mem(text, True, True, 1, k, 1, 100, b2, lt, nh)
         tim = fb.timings()
     finally:
         fb.set_tuning("epoch0", 8192)
+        fb.set_tuning("epoch_mode", 0)
     assert gst == ost and _strip(grecs) == _strip(orecs)
     assert tim["epochs_classify"] > 0 and tim["dry_records"] > ost["reads_processed"] // 2
     assert tim["exact_records"] < ost["reads_processed"]
+
+
+@pytest.mark.parametrize("j", [0, 1, 2])
+def test_query_ext_masks_matches_getValidJExtension(fb, oracle, ref, small_fq, j):
+    """faucet_gpu_query_ext_masks (batched Bloom walks for the contig build) against the reference's own
+    JunctionMap::getValidJExtension (utils/JunctionMap.cpp:474-490) on k-mers of the reads, both orientations, plus
+    random k-mers (mostly non-members)"""
+    _, text = small_fq
+    k = 31
+    lt, nh = _geom(oracle, 100000, 50000)
+    _, b2, _ = oracle.load_two_filters(text, True, k, lt, nh)
+    seqs = [l for l in text.split(b"\n")[1:4000:4] if b"N" not in l and len(l) >= k + 1]
+    kmers = []
+    for s in seqs[:300]:
+        for p in range(0, len(s) - k, 7):
+            x = oracle.first_kmer(s[p:p + k].decode(), k)
+            kmers += [x, oracle.lib.fo_revcomp(x, k)]
+    rng = np.random.default_rng(9)
+    kmers += [int(v) for v in rng.integers(0, 1 << 62, size=2000, dtype=np.uint64)]
+    kmers = np.array(kmers, np.uint64)
+    masks = fb.query_ext_masks(kmers, k, j, b2, lt, nh)
+    valid = masks >> 4
+    ours = np.where(valid == 0, -1, np.where((valid & (valid - 1)) != 0, -2, np.log2(np.maximum(valid, 1)).astype(np.int32)))
+    theirs = ref.valid_j_extension(kmers, k, j, b2, lt, nh)
+    assert np.array_equal(ours, theirs)
+    assert ((masks & 15) | valid == (masks & 15)).all()  # a valid extension is a member
+    # the device copy the call left behind serves the next one (bloo2 = None)
+    assert np.array_equal(fb.query_ext_masks(kmers[:100], k, j, None, lt, nh), masks[:100])

@@ -74,6 +74,19 @@ int main(int argc, char** argv) {
       rn[r] = (uint8_t)(cnt > 32 ? 32 : cnt); r++;
     }
   }
+  { /* depth of the dependency DAG of the dataflow executor: a record runs after every earlier record sharing a slot */
+    uint32_t* last = calloc(RES_MASK + 1ull, 4); uint32_t maxd = 0; double sum = 0;
+    for (uint32_t r = 0; r < R; r++) {
+      uint32_t d = 0;
+      for (int i = 0; i < rn[r]; i++) if (last[rs[(size_t)r * 32 + i]] > d) d = last[rs[(size_t)r * 32 + i]];
+      d++;
+      for (int i = 0; i < rn[r]; i++) last[rs[(size_t)r * 32 + i]] = d;
+      if (d > maxd) maxd = d; sum += d;
+      if ((r + 1) % (R / 10) == 0) fprintf(stderr, "  after %u records: DAG depth %u\n", r + 1, maxd);
+    }
+    fprintf(stderr, "DAG depth %u for %u records (mean level %.1f)\n", maxd, R, sum / R);
+    free(last);
+  }
   uint8_t* writer = calloc(R, 1);
   for (size_t i = 0; i < nW; i++) writer[W[i].rec] = 1;
   uint32_t* dirty = malloc((RES_MASK + 1ull) * 4);

@@ -24,10 +24,10 @@ n = min(raw.size, int(os.environ.get("SWEEP_BYTES", 2 << 30)))
 n = int(np.flatnonzero(raw[:n] == 10)[-1]) + 1 if n < raw.size else n
 n -= 0
 dev = torch.from_numpy(raw[:n]).cuda()
-CONFIGS = [dict(), dict(epoch_mode=0)]
+CONFIGS = [dict(), dict(epoch_mode=1)]
 if os.environ.get("SWEEP"):
     CONFIGS = [json.loads(x) for x in os.environ["SWEEP"].split(";")]
-DEFAULT = dict(stitch_exec=1, epoch_recheck=1, flow_chunk=1 << 20, epoch_mode=1, epoch0=8192, epoch_max=1 << 20, epoch_switch_pct=30, epoch_shrink_pct=14, epoch_grow_pct=6,
+DEFAULT = dict(stitch_exec=1, epoch_recheck=1, flow_chunk=1 << 20, epoch_mode=0, epoch0=8192, epoch_max=1 << 20, epoch_switch_pct=30, epoch_shrink_pct=14, epoch_grow_pct=6,
                stitch_blocks=3, stitch_shrink_den=4, stitch_grow_den=10, stitch_w_max=1 << 15, res_log2=24, table_cap0=1 << 22)
 ref = None
 for cfg in CONFIGS:
@@ -57,5 +57,5 @@ for cfg in CONFIGS:
                       "rounds": t["stitch_rounds"], "deferred": t["stitch_deferred"],
                       "epochs": [t["epochs_exact"], t["epochs_classify"]], "exact_records": t["exact_records"], "dry_records": t["dry_records"],
                       "iterations": t["epoch_iterations"], "nonquiet": t["nonquiet_records"], "writers": t["writer_records"],
-                      "fallbacks": t["epoch_fallbacks"], "reads": st["reads_processed"], "same_result": sig == ref}), flush=True)
+                      "fallbacks": t["epoch_fallbacks"], "phase": t["stitch_phase_ns"], "reads": st["reads_processed"], "same_result": sig == ref}), flush=True)
     s.close()
