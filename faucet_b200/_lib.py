@@ -90,6 +90,7 @@ def _load():
     L.faucet_session_stitch.argtypes = [vp, C.c_int, C.c_int, _u64p]
     L.faucet_session_stitch_begin.argtypes = [vp, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
     L.faucet_session_stitch_batch.argtypes = [vp]
+    L.faucet_session_flow_prepare.argtypes = [vp]
     L.faucet_session_get_bloom.argtypes = [vp, _u8p, _u8p]
     L.faucet_session_set_bloom.argtypes = [vp, _u8p]
     L.faucet_session_read_bloom.argtypes = [vp, _u8p]
@@ -328,7 +329,7 @@ class Session:
         _check(lib.faucet_session_sync(self.h))
 
     # ---- multi-GPU stage API (include/faucet_gpu.h, "multi-GPU") ----
-    BUFFERS = {"inval": 0, "packed": 1, "flags": 2, "seq_start": 3, "seq_end": 4, "bloo1_local": 5, "bloom": 6}
+    BUFFERS = {"inval": 0, "packed": 1, "flags": 2, "seq_start": 3, "seq_end": 4, "bloo1_local": 5, "bloom": 6, "flow_rows": 7, "flow_preds": 8}
 
     def prepare_multi(self):
         _check(lib.faucet_session_prepare_multi(self.h))
@@ -366,6 +367,9 @@ class Session:
     def stitch_begin(self, paired_ends, no_cleaning, spf=None, spf_geom=(0, 0), lpf=None, lpf_geom=(0, 0)):
         _check(lib.faucet_session_stitch_begin(self.h, int(paired_ends), int(no_cleaning), _ptr(spf), spf_geom[0],
                                                spf_geom[1], _ptr(lpf), lpf_geom[0], lpf_geom[1]))
+
+    def flow_prepare(self):
+        _check(lib.faucet_session_flow_prepare(self.h))
 
     def stitch_batch(self):
         _check(lib.faucet_session_stitch_batch(self.h))

@@ -45,7 +45,7 @@ struct Global {
   uint32_t epoch_switch_pct = 30;                // an ordered epoch with fewer writers than this switches to classify epochs
   uint32_t epoch_shrink_pct = 14, epoch_grow_pct = 6;  // exact-set share above / below which the epoch halves / doubles
   int stitch_exec = 1;                           // ordered executor: 1 = dataflow (flow.cuh), 0 = rounds with grid barriers (stitch.cuh)
-  uint32_t flow_chunk = 1u << 20;                // records per dependency sort of the dataflow executor
+  uint32_t flow_chunk = 1u << 22;                // records per dependency sort of the dataflow executor
   bool epoch_recheck = true;                     // records with earlier but no later writes under their slots are walked again on
                                                  // the live table instead of joining the exact set
   int load_memo_log2 = 29;            // pass 1 caches saturated k-mers when the filter has at least 2^this bits
@@ -132,6 +132,11 @@ struct faucet_session {
   unsigned int* d_fbig = nullptr;
   const void* flow_fn = nullptr;
   int flow_grid = 0;
+  // a dependency sort prepared ahead for the whole parsed batch (faucet_session_flow_prepare): in the session's own
+  // buffers, or -- pass 2 on retained planes -- next to the planes pass 1 kept
+  bool prep_valid = false, prep_big = false;
+  uint32_t prep_n = 0;
+  const uint32_t *prep_rows = nullptr, *prep_preds = nullptr;
   uint8_t* d_in_exact = nullptr;  // epochs: per record of the batch, member of the exact set
   size_t in_exact_cap = 0;
   uint32_t *d_list = nullptr, *d_eprefix = nullptr, *d_eprefix_sums = nullptr, *d_count = nullptr;  // the exact set as an ascending list
@@ -160,7 +165,8 @@ struct faucet_session {
   faucet_scan_stats sstats{};
   int stitch_grid = 0;
   // planes of the batches of the last pass 1 (tuning "retain_planes"): pass 2 can run without the text
-  struct Retained { size_t n; uint32_t n_recs; bool fastq; uint32_t *inval, *packed, *seq_start, *seq_end; };
+  struct Retained { size_t n; uint32_t n_recs; bool fastq; uint32_t *inval, *packed, *seq_start, *seq_end;
+                    uint32_t *rows, *preds; bool prep, big; };  // + the dependency sort of the batch, if pass 1 prepared one
   std::vector<Retained> retained;
   struct Arena { uint8_t* p; size_t cap, used; };  // device blocks the retained planes live in; kept across passes
   std::vector<Arena> arena;
@@ -177,6 +183,7 @@ struct faucet_session {
   uint32_t* d_b1local = nullptr;            // OR of every k-mer of this GPU's shard (plain layout)
   int n_ranks = 1, rank = 0;
   void* peer[FAUCET_BUF_COUNT][MAX_PEERS] = {};
+  char peer_handle[FAUCET_BUF_COUNT][MAX_PEERS][FAUCET_IPC_HANDLE_BYTES] = {};
   bool peers_open = false;
   const void* stitch_fn = nullptr;
   // bookkeeping
@@ -504,6 +511,7 @@ int faucet_session_reset_filters(faucet_session* s) {
 }
 
 static int parse_batch(faucet_session* s, bool fastq, bool final_batch) {
+  s->prep_valid = false;  // a dependency sort belongs to one parsed batch
   s->fastq = fastq;
   s->final_batch = final_batch;
   uint32_t n_chunks = (uint32_t)((s->n + PARSE_CHUNK - 1) / PARSE_CHUNK);
@@ -933,35 +941,140 @@ static void exclusive_scan_u32(faucet_session* s, uint32_t* data, unsigned long 
 static int stitch_run_ordered(faucet_session* s, const uint32_t* list, uint32_t begin, uint32_t end, bool mark_dirty,
                               bool allow_grow, bool* need_grow);
 
+static int flow_init(faucet_session* s) {
+  if (s->flow_fn) return 0;
+  int rc, per_sm = 0;
+  const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
+  s->flow_fn = (const void*)stitch_flow_kernel<FAUCET_FLOW_BLOCKS>;
+  CU(cudaFuncSetAttribute(s->flow_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->flow_fn, STITCH_THREADS, smem));
+  if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_flow_kernel cannot be made resident");
+  s->flow_grid = per_sm * g.sm_count;
+  if ((rc = dmalloc(&s->d_fbig, 64))) return rc;  // [0] = long-line count, [32] = the ticket counter (its own 128-byte line)
+  return 0;
+}
+
+static int flow_ensure(faucet_session* s, uint32_t n) {
+  if (n <= s->flow_cap) return 0;
+  int rc;
+  cudaFree(s->d_frows); cudaFree(s->d_fpreds); cudaFree(s->d_fdone); cudaFree(s->d_fcounts); cudaFree(s->d_fcount_sums);
+  s->d_frows = s->d_fpreds = s->d_fdone = s->d_fcounts = s->d_fcount_sums = nullptr;
+  s->prep_valid = false;
+  s->flow_cap = (size_t)n + n / 4 + 1024;
+  if ((rc = dmalloc(&s->d_frows, s->flow_cap * ROW_WORDS)) || (rc = dmalloc(&s->d_fpreds, s->flow_cap * ROW_WORDS)) ||
+      (rc = dmalloc(&s->d_fdone, s->flow_cap)) || (rc = dmalloc(&s->d_fcounts, s->flow_cap + 1)) ||
+      (rc = dmalloc(&s->d_fcount_sums, s->flow_cap / SCAN_CHUNK + 4)))
+    return rc;
+  return 0;
+}
+
+// The dependency sort of the dataflow executor (flow.cuh) for the entries [b0, b0 + n) of `list` (NULL: the records
+// themselves) of the parsed batch: rows and predecessors into the session's buffers.  A pure function of the text
+// planes -- it does not touch the junction table -- so a whole batch can be prepared ahead of its stitch: during pass 1
+// (retained planes), or by the GPU that owns the shard (multi-GPU).  *big: a line has more slots than a row holds.
+static int flow_prepare(faucet_session* s, const uint32_t* list, uint32_t b0, uint32_t n, bool* big_out) {
+  int rc;
+  if ((rc = flow_init(s)) || (rc = flow_ensure(s, n))) return rc;
+  const int grid = g.sm_count * 8;
+  StitchArgs a;
+  stitch_fill_args(s, a);
+  a.list = list ? list + b0 : nullptr;
+  FlowArgs f;
+  std::memset(&f, 0, sizeof f);
+  f.n = n; f.begin = b0; f.rows = s->d_frows; f.preds = s->d_fpreds; f.done = s->d_fdone; f.counts = s->d_fcounts; f.big = s->d_fbig;
+  uint32_t tail[2] = {0, 0};  // last count and its prefix: their sum is the number of pairs
+  unsigned int big = 0;
+  {
+    KTimer kt(s, KT_FLOW_PREP);
+    CU(cudaMemsetAsync(s->d_fbig, 0, 4, s->stream));
+    flow_rows_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(a, f);
+    CU(cudaMemcpyAsync(&tail[0], s->d_fcounts + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+    exclusive_scan_u32(s, s->d_fcounts, n, s->d_fcount_sums);
+    CU(cudaMemcpyAsync(&tail[1], s->d_fcounts + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&big, s->d_fbig, 4, cudaMemcpyDeviceToHost, s->stream));
+    s->launches++;
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  if ((rc = check_launch("flow_rows"))) return rc;
+  *big_out = big != 0;
+  if (big) return 0;
+  const uint32_t n_pairs = tail[0] + tail[1];
+  f.n_pairs = n_pairs;
+  f.n_sub = (n_pairs + RADIX_SUB - 1) / RADIX_SUB;
+  if (n_pairs > s->fpairs_cap) {
+    cudaFree(s->d_fpairs); cudaFree(s->d_fpairs2); s->d_fpairs = s->d_fpairs2 = nullptr;
+    s->fpairs_cap = (size_t)n_pairs + n_pairs / 4 + 1024;
+    if ((rc = dmalloc(&s->d_fpairs, s->fpairs_cap)) || (rc = dmalloc(&s->d_fpairs2, s->fpairs_cap))) return rc;
+  }
+  if ((size_t)f.n_sub * 256 > s->fhist_cap) {
+    cudaFree(s->d_fhist); cudaFree(s->d_fhist_sums); s->d_fhist = s->d_fhist_sums = nullptr;
+    s->fhist_cap = (size_t)f.n_sub * 256 + 1024;
+    if ((rc = dmalloc(&s->d_fhist, s->fhist_cap)) || (rc = dmalloc(&s->d_fhist_sums, s->fhist_cap / SCAN_CHUNK + 4))) return rc;
+  }
+  f.pairs = s->d_fpairs; f.pairs2 = s->d_fpairs2; f.hist = s->d_fhist;
+  {
+    KTimer kt(s, KT_FLOW_PREP);
+    flow_pairs_kernel<<<grid, 256, 0, s->stream>>>(f);
+    s->launches++;
+    if (n_pairs) {
+      const unsigned rgrid = (f.n_sub + RADIX_THREADS / 32 - 1) / (RADIX_THREADS / 32);
+      for (int shift = 0; shift < g.res_log2; shift += 8) {  // stable LSD passes over the slot
+        f.shift = shift;
+        radix_hist_kernel<<<rgrid, RADIX_THREADS, 0, s->stream>>>(f);
+        exclusive_scan_u32(s, s->d_fhist, (unsigned long long)f.n_sub * 256, s->d_fhist_sums);
+        radix_scatter_kernel<<<rgrid, RADIX_THREADS, 0, s->stream>>>(f);
+        std::swap(f.pairs, f.pairs2);
+        s->launches += 2;
+      }
+      flow_preds_kernel<<<grid, 256, 0, s->stream>>>(f);
+      s->launches++;
+    }
+  }
+  return check_launch("flow_prepare");
+}
+
+// prepares the whole parsed batch ahead of its stitch (stage API; pass 1 with retained planes; shard owners)
+int faucet_session_flow_prepare(faucet_session* s) {
+  if (!s->parsed) return fail(FAUCET_E_STATE, "flow_prepare before parse");
+  s->prep_valid = false;
+  if (g.stitch_exec == 0 || s->n_recs == 0 || s->n_recs > g.flow_chunk) return 0;  // nothing to keep: the stitch sorts itself
+  bool big = false;
+  int rc = flow_prepare(s, nullptr, 0, s->n_recs, &big);
+  if (rc) return rc;
+  s->prep_valid = true; s->prep_n = s->n_recs; s->prep_big = big;
+  s->prep_rows = s->d_frows; s->prep_preds = s->d_fpreds;
+  return 0;
+}
+
 // The ordered execution of the entries [begin, end) of `list` (NULL: the records themselves) by the dataflow
-// executor (flow.cuh): dependency sort, then one persistent kernel, in chunks of g.flow_chunk records.  Same
-// contract as stitch_run_ordered, which still takes the lists that hold a line with more slots than a row.
+// executor (flow.cuh): dependency sort (unless the batch came with one), then one persistent kernel, in chunks of
+// g.flow_chunk records.  Same contract as stitch_run_ordered, which still takes the lists that hold a line with
+// more slots than a row.
 static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t begin, uint32_t end, bool mark_dirty,
                            bool allow_grow, bool* need_grow) {
   if (need_grow) *need_grow = false;
   if (g.stitch_exec == 0) return stitch_run_ordered(s, list, begin, end, mark_dirty, allow_grow, need_grow);
   int rc;
-  if (!s->flow_fn) {
-    int per_sm = 0;
-    const size_t smem = STITCH_WARPS * sizeof(WarpScratch);
-    s->flow_fn = (const void*)stitch_flow_kernel<FAUCET_FLOW_BLOCKS>;
-    CU(cudaFuncSetAttribute(s->flow_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->flow_fn, STITCH_THREADS, smem));
-    if (per_sm < 1) return fail(FAUCET_E_CUDA, "stitch_flow_kernel cannot be made resident");
-    s->flow_grid = per_sm * g.sm_count;
-    if ((rc = dmalloc(&s->d_fbig, 64))) return rc;  // [0] = long-line count, [32] = the ticket counter (its own 128-byte line)
-  }
-  const int grid = g.sm_count * 8;
+  if ((rc = flow_init(s))) return rc;
   for (uint32_t b0 = begin; b0 < end;) {
     const uint32_t n = std::min<uint32_t>(end - b0, g.flow_chunk);
-    if (n > s->flow_cap) {
-      cudaFree(s->d_frows); cudaFree(s->d_fpreds); cudaFree(s->d_fdone); cudaFree(s->d_fcounts); cudaFree(s->d_fcount_sums);
-      s->d_frows = s->d_fpreds = s->d_fdone = s->d_fcounts = s->d_fcount_sums = nullptr;
-      s->flow_cap = (size_t)n + n / 4 + 1024;
-      if ((rc = dmalloc(&s->d_frows, s->flow_cap * ROW_WORDS)) || (rc = dmalloc(&s->d_fpreds, s->flow_cap * ROW_WORDS)) ||
-          (rc = dmalloc(&s->d_fdone, s->flow_cap)) || (rc = dmalloc(&s->d_fcounts, s->flow_cap + 1)) ||
-          (rc = dmalloc(&s->d_fcount_sums, s->flow_cap / SCAN_CHUNK + 4)))
-        return rc;
+    const bool prepared = !list && b0 == 0 && n == s->n_recs && s->prep_valid && s->prep_n == n;
+    bool big = false;
+    const uint32_t *rows = s->prep_rows, *preds = s->prep_preds;
+    if (prepared) {
+      big = s->prep_big;
+      if ((rc = flow_ensure(s, n))) return rc;  // (the done flags; a prepared sort in the session's own buffers fits already)
+      if (!s->prep_valid) return fail(FAUCET_E_STATE, "prepared dependency sort lost");
+    } else {
+      if ((rc = flow_prepare(s, list, b0, n, &big))) return rc;
+      s->prep_valid = false;  // the buffers now describe this chunk
+      rows = s->d_frows; preds = s->d_fpreds;
+    }
+    if (big) {  // a line with more slots than a row holds: this chunk goes through the rounds
+      if ((rc = stitch_run_ordered(s, list, b0, b0 + n, mark_dirty, allow_grow, need_grow))) return rc;
+      if (need_grow && *need_grow) return 0;
+      b0 += n;
+      continue;
     }
     StitchArgs a;
     stitch_fill_args(s, a);
@@ -970,60 +1083,9 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
     a.dirty = mark_dirty ? s->d_dirty : nullptr; a.dirty_max = mark_dirty ? s->d_dirty_max : nullptr;
     FlowArgs f;
     std::memset(&f, 0, sizeof f);
-    f.n = n; f.begin = b0; f.rows = s->d_frows; f.preds = s->d_fpreds; f.done = s->d_fdone; f.counts = s->d_fcounts; f.big = s->d_fbig; f.next = s->d_fbig + 32;
-    uint32_t tail[2] = {0, 0};  // last count and its prefix: their sum is the number of pairs
-    unsigned int big = 0;
-    {
-      KTimer kt(s, KT_FLOW_PREP);
-      CU(cudaMemsetAsync(s->d_fbig, 0, 4, s->stream));
-      flow_rows_kernel<<<grid, DRY_THREADS, 0, s->stream>>>(a, f);
-      CU(cudaMemcpyAsync(&tail[0], s->d_fcounts + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
-      exclusive_scan_u32(s, s->d_fcounts, n, s->d_fcount_sums);
-      CU(cudaMemcpyAsync(&tail[1], s->d_fcounts + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
-      CU(cudaMemcpyAsync(&big, s->d_fbig, 4, cudaMemcpyDeviceToHost, s->stream));
-      s->launches++;
-    }
-    CU(cudaStreamSynchronize(s->stream));
-    if ((rc = check_launch("flow_rows"))) return rc;
-    if (big) {  // a line with more slots than a row holds: this chunk goes through the rounds
-      if ((rc = stitch_run_ordered(s, list, b0, b0 + n, mark_dirty, allow_grow, need_grow))) return rc;
-      if (need_grow && *need_grow) return 0;
-      b0 += n;
-      continue;
-    }
-    const uint32_t n_pairs = tail[0] + tail[1];
-    f.n_pairs = n_pairs;
-    f.n_sub = (n_pairs + RADIX_SUB - 1) / RADIX_SUB;
-    if (n_pairs > s->fpairs_cap) {
-      cudaFree(s->d_fpairs); cudaFree(s->d_fpairs2); s->d_fpairs = s->d_fpairs2 = nullptr;
-      s->fpairs_cap = (size_t)n_pairs + n_pairs / 4 + 1024;
-      if ((rc = dmalloc(&s->d_fpairs, s->fpairs_cap)) || (rc = dmalloc(&s->d_fpairs2, s->fpairs_cap))) return rc;
-    }
-    if ((size_t)f.n_sub * 256 > s->fhist_cap) {
-      cudaFree(s->d_fhist); cudaFree(s->d_fhist_sums); s->d_fhist = s->d_fhist_sums = nullptr;
-      s->fhist_cap = (size_t)f.n_sub * 256 + 1024;
-      if ((rc = dmalloc(&s->d_fhist, s->fhist_cap)) || (rc = dmalloc(&s->d_fhist_sums, s->fhist_cap / SCAN_CHUNK + 4))) return rc;
-    }
-    f.pairs = s->d_fpairs; f.pairs2 = s->d_fpairs2; f.hist = s->d_fhist;
-    {
-      KTimer kt(s, KT_FLOW_PREP);
-      flow_pairs_kernel<<<grid, 256, 0, s->stream>>>(f);
-      s->launches++;
-      if (n_pairs) {
-        const unsigned rgrid = (f.n_sub + RADIX_THREADS / 32 - 1) / (RADIX_THREADS / 32);
-        for (int shift = 0; shift < g.res_log2; shift += 8) {  // stable LSD passes over the slot
-          f.shift = shift;
-          radix_hist_kernel<<<rgrid, RADIX_THREADS, 0, s->stream>>>(f);
-          exclusive_scan_u32(s, s->d_fhist, (unsigned long long)f.n_sub * 256, s->d_fhist_sums);
-          radix_scatter_kernel<<<rgrid, RADIX_THREADS, 0, s->stream>>>(f);
-          std::swap(f.pairs, f.pairs2);
-          s->launches += 2;
-        }
-        flow_preds_kernel<<<grid, 256, 0, s->stream>>>(f);
-        s->launches++;
-      }
-      CU(cudaMemsetAsync(s->d_fdone, 0, (size_t)n * 4, s->stream));
-    }
+    f.n = n; f.begin = b0; f.rows = const_cast<uint32_t*>(rows); f.preds = const_cast<uint32_t*>(preds); f.done = s->d_fdone;
+    f.next = s->d_fbig + 32;
+    CU(cudaMemsetAsync(s->d_fdone, 0, (size_t)n * 4, s->stream));
     // ---- run; relaunched after the table grew / the extension lists were drained
     while (true) {
       struct { unsigned int next, nd[2], W, round, status; } z = {0, {0, 0}, s->h_st.W, s->h_st.round, ST_DONE};
@@ -1361,6 +1423,8 @@ static void* session_buffer(faucet_session* s, int what) {
     case FAUCET_BUF_SEQ_END: return s->d_seq_end;
     case FAUCET_BUF_BLOO1_LOCAL: return s->d_b1local;
     case FAUCET_BUF_BLOOM: return s->d_bloom;
+    case FAUCET_BUF_FLOW_ROWS: return s->prep_valid && !s->prep_big ? s->d_frows : nullptr;
+    case FAUCET_BUF_FLOW_PREDS: return s->prep_valid && !s->prep_big ? s->d_fpreds : nullptr;
     default: return nullptr;
   }
 }
@@ -1377,6 +1441,10 @@ int faucet_session_prepare_multi(faucet_session* s) {
 int faucet_session_export(faucet_session* s, int what, void* handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) == FAUCET_IPC_HANDLE_BYTES, "handle size");
   void* p = session_buffer(s, what);
+  if (!p && (what == FAUCET_BUF_FLOW_ROWS || what == FAUCET_BUF_FLOW_PREDS)) {  // no prepared sort: an all-zero handle says so
+    memset(handle_out, 0, FAUCET_IPC_HANDLE_BYTES);
+    return 0;
+  }
   if (!p) return fail(FAUCET_E_STATE, "buffer not allocated yet (call faucet_session_prepare_multi first)");
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, p));
@@ -1388,10 +1456,17 @@ int faucet_session_open_peers(faucet_session* s, int what, const void* handles, 
   if (n_ranks < 1 || n_ranks > MAX_PEERS || my_rank < 0 || my_rank >= n_ranks) return fail(FAUCET_E_ARG, "bad rank layout");
   if (what < 0 || what >= FAUCET_BUF_COUNT) return fail(FAUCET_E_ARG, "bad buffer id");
   s->n_ranks = n_ranks; s->rank = my_rank;
+  static const char zero[FAUCET_IPC_HANDLE_BYTES] = {0};
   for (int r = 0; r < n_ranks; r++) {
     if (r == my_rank) { s->peer[what][r] = session_buffer(s, what); continue; }
+    const char* hb = (const char*)handles + (size_t)r * FAUCET_IPC_HANDLE_BYTES;
+    // (a buffer may be exported again -- the dependency sort moves when a batch outgrows it: same handle, same mapping)
+    if (s->peer[what][r] && !memcmp(hb, s->peer_handle[what][r], FAUCET_IPC_HANDLE_BYTES)) continue;
+    if (s->peer[what][r]) { cudaIpcCloseMemHandle(s->peer[what][r]); s->peer[what][r] = nullptr; }
+    memcpy(s->peer_handle[what][r], hb, FAUCET_IPC_HANDLE_BYTES);
+    if (!memcmp(hb, zero, FAUCET_IPC_HANDLE_BYTES)) continue;  // the peer has nothing to show
     cudaIpcMemHandle_t h;
-    memcpy(&h, (const char*)handles + (size_t)r * FAUCET_IPC_HANDLE_BYTES, sizeof h);
+    memcpy(&h, hb, sizeof h);
     void* p = nullptr;
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->peer[what][r] = p;
@@ -1406,6 +1481,7 @@ int faucet_session_close_peers(faucet_session* s) {
     for (int r = 0; r < s->n_ranks; r++) {
       if (r != s->rank && s->peer[w][r]) cudaIpcCloseMemHandle(s->peer[w][r]);
       s->peer[w][r] = nullptr;
+      memset(s->peer_handle[w][r], 0, FAUCET_IPC_HANDLE_BYTES);
     }
   s->peers_open = false;
   return 0;
@@ -1472,6 +1548,17 @@ int faucet_session_import_planes(faucet_session* s, int peer_rank, size_t n_text
     CU(cudaMemcpyAsync(s->d_flags, s->peer[FAUCET_BUF_FLAGS][peer_rank], (words - 2) * 32, cudaMemcpyDeviceToDevice, s->stream));  // bytes or 8 plane words per 32
     CU(cudaMemcpyAsync(s->d_seq_start, s->peer[FAUCET_BUF_SEQ_START][peer_rank], (size_t)n_recs * 4, cudaMemcpyDeviceToDevice, s->stream));
     CU(cudaMemcpyAsync(s->d_seq_end, s->peer[FAUCET_BUF_SEQ_END][peer_rank], (size_t)n_recs * 4, cudaMemcpyDeviceToDevice, s->stream));
+    // the dependency sort of the shard, if its owner prepared one (faucet_session_flow_prepare)
+    s->prep_valid = false;
+    const void *pr = s->peer[FAUCET_BUF_FLOW_ROWS][peer_rank], *pp = s->peer[FAUCET_BUF_FLOW_PREDS][peer_rank];
+    if (pr && pp && n_recs && n_recs <= g.flow_chunk) {
+      int rc = flow_init(s);
+      if (!rc) rc = flow_ensure(s, n_recs);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(s->d_frows, pr, (size_t)n_recs * ROW_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream));
+      CU(cudaMemcpyAsync(s->d_fpreds, pp, (size_t)n_recs * ROW_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream));
+      s->prep_valid = true; s->prep_n = n_recs; s->prep_big = false; s->prep_rows = s->d_frows; s->prep_preds = s->d_fpreds;
+    }
   }
   s->n = n_text; s->n_recs = n_recs; s->fastq = fastq != 0; s->parsed = true;
   return 0;
@@ -1518,7 +1605,7 @@ static int retained_push(faucet_session* s) {
   const size_t n_chunks = std::max<size_t>(1, (s->n + PARSE_CHUNK - 1) / PARSE_CHUNK);
   const size_t words = n_chunks * (PARSE_CHUNK / 32) + 2;  // what parse_batch covers, guard words included
   const size_t nrec = std::max<size_t>(1, s->n_recs);
-  faucet_session::Retained b{s->n, s->n_recs, s->fastq, nullptr, nullptr, nullptr, nullptr};
+  faucet_session::Retained b{s->n, s->n_recs, s->fastq, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, false};
   if (!(b.inval = retained_alloc(s, words * 4)) || !(b.packed = retained_alloc(s, (2 * words + 2) * 4)) ||
       !(b.seq_start = retained_alloc(s, nrec * 4)) || !(b.seq_end = retained_alloc(s, nrec * 4))) {
     retained_clear(s);
@@ -1528,8 +1615,19 @@ static int retained_push(faucet_session* s) {
   cudaMemcpyAsync(b.packed, s->d_packed, (2 * words + 2) * 4, cudaMemcpyDeviceToDevice, s->stream);
   cudaMemcpyAsync(b.seq_start, s->d_seq_start, nrec * 4, cudaMemcpyDeviceToDevice, s->stream);
   cudaMemcpyAsync(b.seq_end, s->d_seq_end, nrec * 4, cudaMemcpyDeviceToDevice, s->stream);
+  size_t extra = 0;
+  if (s->prep_valid && s->prep_n == s->n_recs) {  // the stitch of this batch will not have to sort
+    b.big = s->prep_big;
+    if (b.big) b.prep = true;
+    else if ((b.rows = retained_alloc(s, nrec * ROW_WORDS * 4)) && (b.preds = retained_alloc(s, nrec * ROW_WORDS * 4))) {
+      cudaMemcpyAsync(b.rows, s->prep_rows, nrec * ROW_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream);
+      cudaMemcpyAsync(b.preds, s->prep_preds, nrec * ROW_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream);
+      b.prep = true;
+      extra = 2 * nrec * ROW_WORDS * 4;
+    }
+  }
   s->retained.push_back(b);
-  s->retained_bytes += (3 * words + 2 + 2 * nrec) * 4;
+  s->retained_bytes += (3 * words + 2 + 2 * nrec) * 4 + extra;
   return 0;
 }
 
@@ -1745,11 +1843,25 @@ static int load_pass(TextSource& src, int fastq, int k, int log2_tai, int n_hash
   uint64_t total_lines = 0;
   retained_clear(s);
   bool keep = g.retain_planes;
+  const bool trace = getenv("FAUCET_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
   rc = for_each_batch(s, src, fastq != 0, &total_lines, [&](size_t, bool) {
+    const double t0 = now();
     int r = faucet_session_load(s);
+    const double t1 = now();
+    // pass 2 will run on these planes: sort its dependencies now, while the copy engine is the bottleneck
+    if (!r && keep && g.epoch_mode == 0) r = faucet_session_flow_prepare(s);
+    const double t2 = now();
     if (!r && keep && retained_push(s)) keep = false;
+    if (trace) {
+      cudaStreamSynchronize(s->stream);
+      fprintf(stderr, "load_pass: batch %zu bytes %u recs at %.2f ms: load issue %.2f prep %.2f push+drain %.2f\n", s->n, s->n_recs,
+              t0 - t_begin, t1 - t0, t2 - t1, now() - t2);
+    }
     return r;
   });
+  if (trace) fprintf(stderr, "load_pass: batches done at %.2f ms\n", now() - t_begin);
   if (rc) { retained_clear(s); return rc; }
   s->retained_valid = keep && g.retain_planes;
   if ((rc = faucet_session_get_bloom(s, bloo2_out, bloo1_out))) return rc;
@@ -1827,13 +1939,14 @@ int faucet_gpu_scan_retained(int paired_ends, int no_cleaning, int k, int j, int
   for (auto& b : s->retained) {  // the session's plane pointers visit the retained batches in stream order
     s->d_inval = b.inval; s->d_packed = b.packed; s->d_seq_start = b.seq_start; s->d_seq_end = b.seq_end;
     s->n = b.n; s->n_recs = b.n_recs; s->fastq = b.fastq; s->parsed = true;
+    s->prep_valid = b.prep; s->prep_n = b.n_recs; s->prep_big = b.big; s->prep_rows = b.rows; s->prep_preds = b.preds;
     const double t0 = now();
     if ((rc = faucet_session_scan_flags(s)) || (rc = faucet_session_stitch_batch(s))) break;
     if (trace) fprintf(stderr, "scan_retained: batch of %zu bytes, %u records: %.2f ms\n", b.n, b.n_recs, now() - t0);
   }
   if (trace) fprintf(stderr, "scan_retained: %zu batches %.2f ms\n", s->retained.size(), now() - t_begin);
   s->d_inval = inval; s->d_packed = packed; s->d_seq_start = ss; s->d_seq_end = se;
-  s->parsed = false;
+  s->parsed = false; s->prep_valid = false;
   if (rc) return rc;
   const double t_collect = now();
   rc = faucet_session_get_junctions(s, recs_out, n_recs_out, stats);

@@ -11,9 +11,10 @@ the read stream.
   pass 1   every rank: parse, OR all k-mers of the shard into a local array; barrier;
            bloo1 := exclusive prefix-OR over ranks (peer HBM over NVLink); exact two-filter load of the
            shard; barrier; in-place OR all-reduce of the per-shard bloo2 arrays; barrier.
-  pass 2   every rank: scan_flags over its shard (pure); barrier; rank 0 stitches shard 0, then pulls the
-           planes of shard 1, 2, ... and stitches them in stream order (the junction map is one
-           sequential state: src/ReadScanner.cpp:61-231); barrier.
+  pass 2   every rank: scan_flags over its shard (pure) and the dependency sort of its records (pure);
+           barrier; rank 0 stitches shard 0, then pulls the planes + sort of shard 1, 2, ... and stitches
+           them in stream order (the junction map is one sequential state: src/ReadScanner.cpp:61-231);
+           barrier.
 """
 import struct
 
@@ -92,13 +93,21 @@ class ShardedJob:
         """pass 2; rank 0 ends up holding the junction map (engine.junctions())"""
         e = self.eng
         e.scan_flags()
+        ahead = hasattr(e, "flow_prepare")
+        if self.rank > 0 and ahead:
+            # the dependency sort of the stitch is a pure function of the shard's text: its owner sorts, rank 0 imports
+            e.flow_prepare()
+        if self.rank == 0:  # shard 0 needs nothing from the others: stitched while they sort
+            e.stitch_begin(paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom)
+            e.stitch_batch()
         e.sync()
+        if ahead:
+            for what in ("flow_rows", "flow_preds"):  # (the buffers may have moved since the last scan: exported each time)
+                e.open_peers(what, self.comm.all_gather_bytes(e.export(what) if self.rank > 0 else bytes(64)), self.world, self.rank)
         n_text, n_recs = e.batch_info()
         infos = [struct.unpack("<QQ", b) for b in self.comm.all_gather_bytes(struct.pack("<QQ", n_text, n_recs))]
         self.comm.barrier()
         if self.rank == 0:
-            e.stitch_begin(paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom)
-            e.stitch_batch()
             for r in range(1, self.world):
                 e.import_planes(r, infos[r][0], infos[r][1], fastq)
                 e.stitch_batch()

@@ -175,6 +175,11 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
                                 int spf_log2_tai, int spf_n_hash, uint8_t* long_pf, int lpf_log2_tai,
                                 int lpf_n_hash);
 int faucet_session_stitch_batch(faucet_session* s);
+/* The dependency sort of the dataflow executor (per-record predecessor lists) is a pure function of the parsed text:
+ * it may be computed ahead of the stitch of the batch -- pass 1 does so when it retains the planes, and in a
+ * multi-GPU job the GPU that owns a shard does it before rank 0 imports the shard.  Optional: stitch_batch sorts
+ * itself when the batch comes without. */
+int faucet_session_flow_prepare(faucet_session* s);
 int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_t total_lines);
 int faucet_session_set_profiling(faucet_session* s, int on);   /* per-kernel CUDA-event timing */
 int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* bloo1_out);
@@ -201,7 +206,10 @@ int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64
  * Pass 2: scan_flags on every rank; rank 0 stitches its own shard, then import_planes(r) + stitch_batch
  * for r = 1..N-1 (the junction map lives on rank 0). */
 enum { FAUCET_BUF_INVAL = 0, FAUCET_BUF_PACKED, FAUCET_BUF_FLAGS, FAUCET_BUF_SEQ_START, FAUCET_BUF_SEQ_END,
-       FAUCET_BUF_BLOO1_LOCAL, FAUCET_BUF_BLOOM, FAUCET_BUF_COUNT };
+       FAUCET_BUF_BLOO1_LOCAL, FAUCET_BUF_BLOOM,
+       FAUCET_BUF_FLOW_ROWS, FAUCET_BUF_FLOW_PREDS, /* the dependency sort of the shard (faucet_session_flow_prepare);
+                                                       exported again per scan -- an all-zero handle = none */
+       FAUCET_BUF_COUNT };
 #define FAUCET_IPC_HANDLE_BYTES 64
 int faucet_session_prepare_multi(faucet_session* s);   /* allocates every exportable buffer */
 int faucet_session_export(faucet_session* s, int what, void* handle_out /* 64 bytes */);

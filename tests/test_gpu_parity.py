@@ -42,7 +42,7 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
-EPOCH_DEFAULTS = {"epoch_mode": 0, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 20}
+EPOCH_DEFAULTS = {"epoch_mode": 0, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 22}
 EPOCH_SCHEDULES = {
     "adaptive": {"epoch_mode": 1},                                      # ordered epochs first, then classify epochs
     "ordered_only": {},                                                 # the default: every record through the dataflow executor

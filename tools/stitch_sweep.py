@@ -27,7 +27,7 @@ dev = torch.from_numpy(raw[:n]).cuda()
 CONFIGS = [dict(), dict(epoch_mode=1)]
 if os.environ.get("SWEEP"):
     CONFIGS = [json.loads(x) for x in os.environ["SWEEP"].split(";")]
-DEFAULT = dict(stitch_exec=1, epoch_recheck=1, flow_chunk=1 << 20, epoch_mode=0, epoch0=8192, epoch_max=1 << 20, epoch_switch_pct=30, epoch_shrink_pct=14, epoch_grow_pct=6,
+DEFAULT = dict(stitch_exec=1, epoch_recheck=1, flow_chunk=1 << 22, epoch_mode=0, epoch0=8192, epoch_max=1 << 20, epoch_switch_pct=30, epoch_shrink_pct=14, epoch_grow_pct=6,
                stitch_blocks=3, stitch_shrink_den=4, stitch_grow_den=10, stitch_w_max=1 << 15, res_log2=24, table_cap0=1 << 22)
 ref = None
 for cfg in CONFIGS:
