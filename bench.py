@@ -128,29 +128,39 @@ def survey_bytes(w, n_hash, weight2, r_contained):
     return a_load, a_scan
 
 
-def kernel_bytes(w, n_hash, weight2, r_contained, text_per_kmer):
-    """algorithmic bytes per k-mer of every kernel of THIS implementation, DRAM sectors of 32 bytes
-    for every random access:
+L2_BYTES = 100e6  # what of the 126 MB L2 a randomly probed structure can count on
+
+
+def kernel_bytes(w, n_hash, lt, r_contained, text_per_kmer, junctions):
+    """Algorithmic HBM bytes per k-mer of every kernel of THIS implementation.  Streams are
+    counted in full; a randomly probed structure costs one 32-byte DRAM sector per probe -- but only when it does not
+    fit in L2 (at configs[0..2] the Bloom arrays, and at configs[0..1] the junction keys, are L2 resident: SURVEY H5).
       parse        the text in, 3/8 of it out (validity + 2-bit planes)
-      load_A/B     the planes in + one 32-byte sector of the fused {bloo1, bloo2} array per probe (SURVEY's A_load without
-                   the raw text: n (1 + r) probes)
-      scan_flags   planes in, one flag byte out per text byte, one 8-byte memo word (a 32-byte sector) per k-mer
-      stitch       planes + flags in, two 32-byte key sectors per k-mer position (both orientations), and per record
-                   its predecessor / slot rows (256 B), one done flag and ~2 record sectors per landing (~5)
-      flow_prep    ~15 (slot, record) pairs of 8 bytes per record, read and written once per radix pass (3) plus rows
-    """
+      load_A/B     the planes in; n (1 + r) probes of the fused {bloo1, bloo2} array (2 tai / 8 bytes)
+      scan_flags   planes in, one flag byte out per text byte, one probe of the memo (tai / 2 entries of 8 bytes) per k-mer
+      stitch       planes + flags in; two probes of the key array per k-mer position (both orientations); per record its
+                   slot / predecessor rows (256 B), a done flag and two 32-byte record sectors per landing (~5)
+      flow_prep    per record: its code words, ~15 (slot, record) pairs of 8 bytes read and written per radix pass (3), rows
+    Returns (bytes per k-mer, {structure: resident in L2?})."""
     kpr = w["length"] - w["k"] + 1  # k-mers per record
     planes = 0.375 * text_per_kmer
-    return {
+    tai = 1 << lt
+    cap = 1 << 22
+    while cap // 2 < junctions + 1_100_000:
+        cap *= 2
+    res = {"bloom_fused": 2 * tai / 8 <= L2_BYTES, "scan_memo": max(tai // 2, 1 << 20) * 8 <= L2_BYTES, "junction_keys": cap * 8 <= L2_BYTES}
+    sec = lambda resident: 0.0 if resident else 32.0  # noqa: E731
+    model = {
         "parse": 1.375 * text_per_kmer,
-        "load_A": planes + 32 * n_hash * (1 + r_contained),
+        "load_A": planes + sec(res["bloom_fused"]) * n_hash * (1 + r_contained),
         "load_B": planes,
-        "scan_flags": planes + text_per_kmer + 32.0,
-        "stitch": planes + text_per_kmer + 64.0 + (256 + 32 + 5 * 64) / kpr,
-        "stitch_dry": planes + text_per_kmer + 64.0 + (128 + 5 * 32) / kpr,
+        "scan_flags": planes + text_per_kmer + sec(res["scan_memo"]),
+        "stitch": planes + text_per_kmer + 2 * sec(res["junction_keys"]) + (256 + 32 + 5 * 64) / kpr,
+        "stitch_dry": planes + text_per_kmer + 2 * sec(res["junction_keys"]) + (128 + 5 * 32) / kpr,
         "stitch_verify": 128.0 / kpr,
-        "stitch_flow_prep": (planes + 15 * 8 * 2 * 3 + 256) / kpr,
+        "stitch_flow_prep": planes + (15 * 8 * 2 * 3 + 256) / kpr,
     }
+    return model, res
 
 
 def cpu_geometry(w):
@@ -467,7 +477,7 @@ def run_ours(args, w):
         a_load, a_scan = survey_bytes(w, nh, weight2, r_contained)
         text_per_kmer = n_text / max(1, kmers_per_pass)
         per_step = {n: v[0] / args.steps for n, v in kernel_ms.items()}
-        model = kernel_bytes(w, nh, weight2, r_contained, text_per_kmer)
+        model, l2_resident = kernel_bytes(w, nh, lt, r_contained, text_per_kmer, int(n_junc))
         dom = max(per_step, key=lambda n: per_step[n])        # the kernel with the most time per step
         achieved = kmers_per_pass * model[dom] / (per_step[dom] * 1e-3) / 1e9
         value = kmers_all * args.steps / (ms_all * 1e-3)
@@ -501,6 +511,7 @@ def run_ours(args, w):
                          # would move per k-mer, A_load + A_scan, at this k-mer rate per GPU)
                          "per_kernel_frac": {n: (kmers_per_pass * model[n] / (per_step[n] * 1e-3) / 1e9 / peak) if per_step[n] > 0 else None
                                              for n in per_step},
+                         "l2_resident": l2_resident,
                          "survey_bytes_per_kmer": a_load + a_scan,
                          "survey_path_frac": (value / world) * (a_load + a_scan) / 1e9 / peak},
             "kernels_ms_per_step": per_step,

@@ -518,12 +518,17 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
   OutList o;
   const bool pairs = !a.no_cleaning && a.spf != nullptr;
   const bool want_ext = a.ext != nullptr;
+  uint32_t n_jcheck = 0, n_processed = 0, n_skipped = 0;  // warp-uniform; added to the record's counters at the end
 
   while (true) {
     // ---- find_next_junction (:61-86): 32 half-steps per warp iteration
     bool found = false;
     int slot = -1;
-    while (tp < tested_end) {
+    if (FAST && have_last && tp < tested_end) {  // after a skip the cursor normally stands on the next known junction
+      slot = c.S->slot[2 * rel + tp];
+      found = slot >= 0;
+    }
+    while (!found && tp < tested_end) {
       const int t = tp + lane;
       const bool active = t < tested_end;
       bool known = false, spc = false, tst = false;
@@ -551,27 +556,29 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       const uint32_t upto = hit < 32 ? (hit == 31 ? 0xffffffffu : ((2u << hit) - 1u)) : am;
       // NbJCheckKmer (:46): every half-step that reached testForJunction, the hit one included
       uint32_t jc = (active && ((upto >> lane) & 1u) && !known && !spc) ? cnt : 0u;
-      jc = __reduce_add_sync(0xffffffffu, jc);
-      if (lane == 0) c.cnt[SS_JCHECK] += jc;
+      n_jcheck += __reduce_add_sync(0xffffffffu, jc);
       if (hb) {
-        if (lane == 0) c.cnt[SS_PROCESSED] += hit;
+        n_processed += hit;
         tp += hit;
         slot = __shfl_sync(0xffffffffu, sl, hit);
         found = true;
         break;
       }
-      if (lane == 0) c.cnt[SS_PROCESSED] += __popc(am);
+      n_processed += __popc(am);
       tp += 32;
     }
     if (!found) break;
     // ---- the junction at half-step tp (:134-192)
     const int pos = tp >> 1, dir = tp & 1;
-    const uint64_t fwd = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
-    const uint64_t key = dir ? fwd : revcomp(fwd, k);
+    const bool known = slot >= 0;
+    uint64_t key = 0;  // needed to create the junction, to mark a write (epochs) and for the pair filters
+    if (!known || a.dirty || pairs || want_ext) {
+      const uint64_t fwd = FAST ? line_kmer(a, c, rel + pos) : kmer_at_t<false>(a.packed, s0 + pos, k);
+      key = dir ? fwd : revcomp(fwd, k);
+    }
     const int real = dir ? (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base)
                          : (int)nt_comp(code_at_t<FAST>(c.pk, s0 + pos - 1 - c.pk_base));
     const int fwd_idx = dir ? real : 4, back_idx = dir ? 4 : real;  // getExtensionIndex (utils/ReadKmer.cpp:95-100)
-    const bool known = slot >= 0;
     bool created = false;
     if (!known) {
       if (lane == 0) {
@@ -618,7 +625,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       cur.ok = false;
     }
     if (dist < 1) dist = 1;
-    if (lane == 0) { c.cnt[SS_PROCESSED] += 1; c.cnt[SS_SKIPPED] += (unsigned long long)(dist - 1); }
+    n_processed += 1; n_skipped += (uint32_t)(dist - 1);
     line_visit(c, slot, lane);
     if (wr) {
       c.wrote = true;
@@ -673,6 +680,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
     }
     if (wr) { c.wrote = true; mark_written(a, last_key, c.rec, false, true, lane); }
   }
+  if (lane == 0) { c.cnt[SS_JCHECK] += n_jcheck; c.cnt[SS_PROCESSED] += n_processed; c.cnt[SS_SKIPPED] += n_skipped; }
   __syncwarp();
   out_finish(a, o, pairs, lane);
 }
