@@ -36,7 +36,7 @@ WORKLOADS = {
 }
 J, MAX_SPACER, FP = 1, 100, 0.04  # faucet defaults: -j 1, -max_spacer_dist 100, -fp 0.04 (src/Faucet.h:14-48)
 METRIC = "k-mers/sec (Bloom load + junction scan)"
-KERNELS = ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry", "stitch_verify", "stitch_flow_prep")
+KERNELS = ("parse", "load_A", "load_B", "scan_flags", "stitch", "stitch_dry", "stitch_verify", "stitch_flow_prep", "shard_copy", "shard_merge")
 
 
 def gen_dataset(w, seed, pairs=None, tag="", stream=0, genome=None):
@@ -128,10 +128,11 @@ def survey_bytes(w, n_hash, weight2, r_contained):
     return a_load, a_scan
 
 
+SHARD_PREFIX_PCT = 100  # share of shard 0 that GPU 0 stitches in order before the sharded epoch starts
 L2_BYTES = 100e6  # what of the 126 MB L2 a randomly probed structure can count on
 
 
-def kernel_bytes(w, n_hash, lt, r_contained, text_per_kmer, junctions):
+def kernel_bytes(w, n_hash, lt, r_contained, text_per_kmer, junctions, kmers=1):
     """Algorithmic HBM bytes per k-mer of every kernel of THIS implementation.  Streams are
     counted in full; a randomly probed structure costs one 32-byte DRAM sector per probe -- but only when it does not
     fit in L2 (at configs[0..2] the Bloom arrays, and at configs[0..1] the junction keys, are L2 resident: SURVEY H5).
@@ -159,6 +160,10 @@ def kernel_bytes(w, n_hash, lt, r_contained, text_per_kmer, junctions):
         "stitch_dry": planes + text_per_kmer + 2 * sec(res["junction_keys"]) + (128 + 5 * 32) / kpr,
         "stitch_verify": 128.0 / kpr,
         "stitch_flow_prep": planes + (15 * 8 * 2 * 3 + 256) / kpr,
+        # sharded epoch, per k-mer of ONE shard: the table comes in once (keys + records, written locally) / the owner reads
+        # keys + 16 bytes of counts per slot of every replica (bench: up to 8)
+        "shard_copy": 2 * 72.0 * cap / max(1, kmers),
+        "shard_merge": 24.0 * cap / max(1, kmers),
     }
     return model, res
 
@@ -244,7 +249,8 @@ def sharded_parity_check(fb, torch, dist, rank, world, local):
     shards = fb.plan_shards(text, True, world)
     a, b = shards[rank]
     s = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=max(y - x for x, y in shards) + 1024)
-    job = ShardedJob(s, TorchComm(torch.device("cuda", local)))
+    job = ShardedJob(s, TorchComm(torch.device("cuda", local)), sharded_stitch=os.environ.get("FAUCET_SHARD", "1") != "0",
+                     prefix_pct=int(os.environ.get("FAUCET_SHARD_PREFIX_PCT", str(SHARD_PREFIX_PCT))))
     job.setup()
     s.set_text(text[a:b])
     job.load(True)
@@ -319,7 +325,9 @@ def run_ours(args, w):
     job = None
     if world > 1:
         from faucet_b200.multi import ShardedJob, TorchComm
-        job = ShardedJob(sess, TorchComm(torch.device("cuda", local)))
+        # FAUCET_SHARD=0: the serial stitch on GPU 0; FAUCET_SHARD_PREFIX_PCT: share of shard 0 run in order before the epoch
+        job = ShardedJob(sess, TorchComm(torch.device("cuda", local)), sharded_stitch=os.environ.get("FAUCET_SHARD", "1") != "0",
+                         prefix_pct=int(os.environ.get("FAUCET_SHARD_PREFIX_PCT", str(SHARD_PREFIX_PCT))))
         job.setup()
 
     def step_parts(base):  # several batches through the stage API (load accumulates; one junction map)
@@ -457,8 +465,11 @@ def run_ours(args, w):
         extra["e2e_cleaning"] = {"value": kmers_per_pass / ec, "unit": "k-mers/s", "steps": 1,
                                  "api": "..._mem + faucet_gpu_scan_retained(no_cleaning=0, short + long pair filters)",
                                  "junctions": len(rc_)}
+    scan_ranks = None
     if job is not None:
         barrier()
+        scan_ranks = [None] * world  # every rank's host-side phase times of its last scan (ms)
+        dist.all_gather_object(scan_ranks, (job.last_scan or {}).get("ms", {}))
         sess.close_peers()
         sess.close()
 
@@ -477,7 +488,7 @@ def run_ours(args, w):
         a_load, a_scan = survey_bytes(w, nh, weight2, r_contained)
         text_per_kmer = n_text / max(1, kmers_per_pass)
         per_step = {n: v[0] / args.steps for n, v in kernel_ms.items()}
-        model, l2_resident = kernel_bytes(w, nh, lt, r_contained, text_per_kmer, int(n_junc))
+        model, l2_resident = kernel_bytes(w, nh, lt, r_contained, text_per_kmer, int(n_junc), kmers_per_pass)
         dom = max(per_step, key=lambda n: per_step[n])        # the kernel with the most time per step
         achieved = kmers_per_pass * model[dom] / (per_step[dom] * 1e-3) / 1e9
         value = kmers_all * args.steps / (ms_all * 1e-3)
@@ -491,7 +502,7 @@ def run_ours(args, w):
                        "junctions": int(n_junc), "resident_batches": len(parts),
                        "l2": "inputs (%.0f MB text + planes) exceed the 126 MB L2" % (n_text / 1e6),
                        "parallelism": ("%d contiguous shards of one read stream (one per GPU): exact P2P prefix-OR / OR all-reduce "
-                                       "of the Bloom filters over NVLink, junction stitch on GPU 0" % world) if world > 1 else "single GPU"},
+                                       "of the Bloom filters over NVLink; junction stitch: %s" % (world, (job.last_scan or {}).get("mode", "serial on GPU 0"))) if world > 1 else "single GPU"},
             "e2e": {"value": kmers_all / (e2e_ms_all * 1e-3), "unit": "k-mers/s",
                     "h2d_bytes_per_step": ((2 * n_text + bloo2.nbytes) if two_uploads else n_text) if world == 1 else n_text,
                     "api": ("faucet_gpu_load_two_filters_mem + faucet_gpu_scan_" + ("mem" if two_uploads else "retained")) if world == 1
@@ -519,6 +530,8 @@ def run_ours(args, w):
         }
         if parity is not None:
             out["parity_check"] = parity
+        if job is not None:
+            out["stitch_across_gpus"] = dict(job.last_scan or {"mode": "serial"}, ms_by_rank=scan_ranks)
         if args.cpu_baseline:
             kind, ck, times, sample = cpu_reference_sample(w, lt, nh)
             out["cpu_baseline"] = {"value": ck / times[0], "unit": "k-mers/s", "cores": 1, "kind": kind, "sample": sample}

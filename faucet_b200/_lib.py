@@ -113,6 +113,17 @@ def _load():
     L.faucet_session_import_planes.argtypes = [vp, C.c_int, C.c_size_t, C.c_uint32, C.c_int]
     L.faucet_session_batch_info.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
     L.faucet_host_plan_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, _u64p]
+    u32p = C.POINTER(C.c_uint32)
+    L.faucet_session_stitch_records.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_int]
+    L.faucet_session_shard_rows.argtypes = [vp, C.c_uint32]
+    L.faucet_session_shard_info.argtypes = [vp, C.c_uint32, C.c_int, C.c_void_p]
+    L.faucet_session_shard_begin.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, u32p]
+    L.faucet_session_shard_execute.argtypes = [vp, u32p, C.c_int, C.POINTER(C.c_int)]
+    L.faucet_session_shard_verify.argtypes = [vp, u32p]
+    L.faucet_session_shard_finish.argtypes = [vp, _u64p]
+    L.faucet_session_shard_merge.argtypes = [vp, _u64p]
+    L.faucet_session_shard_end.argtypes = [vp]
+    L.faucet_session_shard_abort.argtypes = [vp]
     return L
 
 
@@ -259,7 +270,8 @@ def scan(path, fastq, paired_ends, no_cleaning, k, j, max_spacer_dist, bloo2, lo
 
 class Session:
     """device-resident stage API (faucet_session_* in include/faucet_gpu.h)"""
-    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4, "stitch_dry": 5, "stitch_verify": 6, "stitch_flow_prep": 7}
+    KERNELS = {"parse": 0, "load_A": 1, "load_B": 2, "scan_flags": 3, "stitch": 4, "stitch_dry": 5, "stitch_verify": 6, "stitch_flow_prep": 7,
+               "shard_copy": 8, "shard_merge": 9}
 
     def __init__(self, k, log2_tai, n_hash, j=1, max_spacer_dist=100, max_text_bytes=1 << 30):
         self.h = C.c_void_p()
@@ -329,7 +341,8 @@ class Session:
         _check(lib.faucet_session_sync(self.h))
 
     # ---- multi-GPU stage API (include/faucet_gpu.h, "multi-GPU") ----
-    BUFFERS = {"inval": 0, "packed": 1, "flags": 2, "seq_start": 3, "seq_end": 4, "bloo1_local": 5, "bloom": 6, "flow_rows": 7, "flow_preds": 8}
+    BUFFERS = {"inval": 0, "packed": 1, "flags": 2, "seq_start": 3, "seq_end": 4, "bloo1_local": 5, "bloom": 6, "flow_rows": 7, "flow_preds": 8,
+               "tbl_keys": 9, "tbl_recs": 10, "jslot": 11, "exact_list": 12, "cov_delta": 13}
 
     def prepare_multi(self):
         _check(lib.faucet_session_prepare_multi(self.h))
@@ -373,6 +386,52 @@ class Session:
 
     def stitch_batch(self):
         _check(lib.faucet_session_stitch_batch(self.h))
+
+    # ---- the stitch across GPUs: the sharded epoch (include/faucet_gpu.h, faucet_b200/csrc/shard.cuh) ----
+    SHARD_INFO_BYTES, SHARD_STATS = 512, 32
+
+    def stitch_records(self, begin, end, advance):
+        _check(lib.faucet_session_stitch_records(self.h, begin, end, int(advance)))
+
+    def shard_rows(self, r_begin):
+        _check(lib.faucet_session_shard_rows(self.h, r_begin))
+
+    def shard_info(self, r_begin, is_owner):
+        buf = C.create_string_buffer(self.SHARD_INFO_BYTES)
+        _check(lib.faucet_session_shard_info(self.h, r_begin, int(is_owner), buf))
+        return buf.raw
+
+    def shard_begin(self, infos, n_ranks, my_rank, owner=0):
+        blob, n = b"".join(infos), C.c_uint32()
+        assert len(blob) == self.SHARD_INFO_BYTES * n_ranks
+        _check(lib.faucet_session_shard_begin(self.h, blob, n_ranks, my_rank, owner, C.byref(n)))
+        return n.value
+
+    def shard_execute(self, counts, it):
+        arr, grow = (C.c_uint32 * len(counts))(*counts), C.c_int()
+        _check(lib.faucet_session_shard_execute(self.h, arr, it, C.byref(grow)))
+        return grow.value
+
+    def shard_verify(self):
+        n = C.c_uint32()
+        _check(lib.faucet_session_shard_verify(self.h, C.byref(n)))
+        return n.value
+
+    def shard_finish(self):
+        st = (C.c_uint64 * self.SHARD_STATS)()
+        _check(lib.faucet_session_shard_finish(self.h, st))
+        return bytes(st)
+
+    def shard_merge(self, stats_all):
+        blob = b"".join(stats_all)
+        arr = (C.c_uint64 * (len(blob) // 8)).from_buffer_copy(blob)
+        _check(lib.faucet_session_shard_merge(self.h, arr))
+
+    def shard_end(self):
+        _check(lib.faucet_session_shard_end(self.h))
+
+    def shard_abort(self):
+        _check(lib.faucet_session_shard_abort(self.h))
 
     @property
     def stream(self):

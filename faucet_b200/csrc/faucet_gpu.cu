@@ -21,6 +21,7 @@
 #include "pair_filter_host.hpp"
 #include "stitch.cuh"
 #include "flow.cuh"
+#include "shard.cuh"
 
 using namespace faucet;
 
@@ -54,6 +55,8 @@ struct Global {
   bool retain_planes = false;         // pass 1 keeps the parsed planes of every batch in HBM for faucet_gpu_scan_retained
   size_t retain_budget = (size_t)64 << 30;
   unsigned long long ext_cap0 = 1ull << 24;
+  bool dry_lazy = true;               // read-only walks look junction keys up as they reach them (no parked line: 10.3 vs 13.5 ms per 1.8 M records)
+  bool shard_force_abort = false;     // tests: the first exact run of a sharded epoch reports "table must grow"
   size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
   faucet_timings tim{};
   faucet_session* cached = nullptr;
@@ -72,7 +75,7 @@ int fail(int code, const std::string& msg) {
 
 constexpr size_t TAIL_MAX = (size_t)1 << 24;  // longest partial record carried between batches
 constexpr size_t TEXT_PAD = 2 * PARSE_CHUNK;
-enum { KT_PARSE = 0, KT_LOAD_A, KT_LOAD_B, KT_SCAN, KT_STITCH, KT_DRY, KT_VERIFY, KT_FLOW_PREP, KT_COUNT };
+enum { KT_PARSE = 0, KT_LOAD_A, KT_LOAD_B, KT_SCAN, KT_STITCH, KT_DRY, KT_VERIFY, KT_FLOW_PREP, KT_SHARD_COPY, KT_SHARD_MERGE, KT_COUNT };
 
 }  // namespace
 
@@ -179,6 +182,25 @@ struct faucet_session {
   unsigned long long hist_cap = 0;
   faucet_junction_rec* d_out = nullptr;
   size_t out_cap = 0;
+  // sharded epoch (shard.cuh): this GPU's own coverage counts / scan counters of its quiet records, a peer's exact list
+  uint32_t* d_cov_delta = nullptr;          // 4 u32 per table slot
+  unsigned long long cov_delta_cap = 0;
+  StitchState* d_st_quiet = nullptr;
+  uint32_t rows_ahead_n = 0, rows_ahead_begin = 0;  // d_rows holds the rows of the records [begin, n) of the parsed batch (shard_rows)
+  bool rows_ahead = false;
+  // the gathered exact set: a small local batch of the lines of all its members (shard.cuh)
+  uint32_t *mb_inval = nullptr, *mb_packed = nullptr, *mb_seq_start = nullptr, *mb_seq_end = nullptr, *mb_gid = nullptr, *mb_span = nullptr,
+           *mb_span_sums = nullptr;
+  uint8_t* mb_flags = nullptr;
+  size_t mb_entries_cap = 0, mb_pos_cap = 0;
+  const uint32_t* cur_gid = nullptr;        // global record indices of the batch the executor runs (NULL: rec_base + index)
+  struct Shard {
+    bool active = false, snapshot = false, ran = false;
+    int owner = 0;
+    uint32_t r_begin = 0;                   // this GPU's records [r_begin, n_recs) belong to the epoch
+    uint64_t rec_base[MAX_PEERS + 1] = {};  // global index of record 0 of every shard; [n_ranks] = records of the stream
+    uint32_t n_recs[MAX_PEERS] = {};
+  } shard;
   // multi-GPU: peer buffers mapped through CUDA IPC (multi.cuh)
   uint32_t* d_b1local = nullptr;            // OR of every k-mer of this GPU's shard (plain layout)
   int n_ranks = 1, rank = 0;
@@ -368,6 +390,10 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
   } else if (n == "ext_cap0") {
     if (value < 64) return fail(FAUCET_E_ARG, "ext_cap0 out of range");
     g.ext_cap0 = value;
+  } else if (n == "dry_lazy") {
+    g.dry_lazy = value != 0;
+  } else if (n == "shard_force_abort") {
+    g.shard_force_abort = value != 0;
   } else {
     return fail(FAUCET_E_ARG, "unknown tuning knob: " + n);
   }
@@ -436,7 +462,8 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_frows); cudaFree(s->d_fpreds); cudaFree(s->d_fdone); cudaFree(s->d_fcounts); cudaFree(s->d_fcount_sums);
   cudaFree(s->d_fpairs); cudaFree(s->d_fpairs2); cudaFree(s->d_fhist); cudaFree(s->d_fhist_sums); cudaFree(s->d_fbig); cudaFree(s->d_in_exact);
   cudaFree(s->d_list); cudaFree(s->d_eprefix); cudaFree(s->d_eprefix_sums); cudaFree(s->d_count); cudaFree(s->d_snap_keys); cudaFree(s->d_snap_recs);
-  cudaFree(s->d_st_snap); cudaFree(s->d_spf_snap);
+  cudaFree(s->d_st_snap); cudaFree(s->d_spf_snap); cudaFree(s->d_cov_delta); cudaFree(s->d_st_quiet);
+  cudaFree(s->mb_inval); cudaFree(s->mb_packed); cudaFree(s->mb_seq_start); cudaFree(s->mb_seq_end); cudaFree(s->mb_gid); cudaFree(s->mb_span); cudaFree(s->mb_span_sums); cudaFree(s->mb_flags);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   faucet_session_close_peers(s);
   cudaFree(s->d_b1local); cudaFree(s->d_hist); cudaFree(s->d_hist_sums); cudaFree(s->d_out);
@@ -512,6 +539,7 @@ int faucet_session_reset_filters(faucet_session* s) {
 
 static int parse_batch(faucet_session* s, bool fastq, bool final_batch) {
   s->prep_valid = false;  // a dependency sort belongs to one parsed batch
+  s->rows_ahead = false;
   s->fastq = fastq;
   s->final_batch = final_batch;
   uint32_t n_chunks = (uint32_t)((s->n + PARSE_CHUNK - 1) / PARSE_CHUNK);
@@ -857,7 +885,7 @@ int faucet_session_stitch_begin(faucet_session* s, int paired_ends, int no_clean
 static void stitch_fill_args(faucet_session* s, StitchArgs& a) {
   std::memset(&a, 0, sizeof a);
   a.inval = s->d_inval; a.packed = s->d_packed; a.flags = s->d_flags;
-  a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base;
+  a.seq_start = s->d_seq_start; a.seq_end = s->d_seq_end; a.n_recs = s->n_recs; a.rec_base = s->rec_base; a.gid = s->cur_gid;
   a.k = s->k; a.j = s->j; a.spacer = s->max_spacer; a.no_cleaning = s->no_cleaning; a.paired = s->paired;
   a.keys = s->d_keys; a.recs = s->d_recs; a.stamps = s->d_jstamps; a.cap = s->tbl_cap;
   a.res = s->d_res; a.res_mask = (uint32_t)(((size_t)1 << g.res_log2) - 1);
@@ -867,6 +895,8 @@ static void stitch_fill_args(faucet_session* s, StitchArgs& a) {
   a.ext = s->lpf.enabled() ? s->d_ext : nullptr; a.ext_cap = s->ext_cap;
   a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
   a.shrink_den = g.stitch_shrink_den; a.grow_den = g.stitch_grow_den;
+  a.cov_stride = REC_WORDS; a.cov_off = REC_COV;
+  a.lazy = g.dry_lazy ? 1 : 0;
 }
 
 // moves what the kernels left in the extension-list buffer to the host
@@ -1058,7 +1088,8 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
   if ((rc = flow_init(s))) return rc;
   for (uint32_t b0 = begin; b0 < end;) {
     const uint32_t n = std::min<uint32_t>(end - b0, g.flow_chunk);
-    const bool prepared = !list && b0 == 0 && n == s->n_recs && s->prep_valid && s->prep_n == n;
+    // (a dependency sort of the whole batch also serves any prefix of it: predecessors are earlier records)
+    const bool prepared = !list && b0 == 0 && s->prep_valid && s->prep_n == s->n_recs && n <= s->prep_n && end <= g.flow_chunk;
     bool big = false;
     const uint32_t *rows = s->prep_rows, *preds = s->prep_preds;
     if (prepared) {
@@ -1425,6 +1456,11 @@ static void* session_buffer(faucet_session* s, int what) {
     case FAUCET_BUF_BLOOM: return s->d_bloom;
     case FAUCET_BUF_FLOW_ROWS: return s->prep_valid && !s->prep_big ? s->d_frows : nullptr;
     case FAUCET_BUF_FLOW_PREDS: return s->prep_valid && !s->prep_big ? s->d_fpreds : nullptr;
+    case FAUCET_BUF_TBL_KEYS: return s->d_keys;
+    case FAUCET_BUF_TBL_RECS: return s->d_recs;
+    case FAUCET_BUF_JSLOT: return s->d_jslot;
+    case FAUCET_BUF_EXACT_LIST: return s->d_list;
+    case FAUCET_BUF_COV_DELTA: return s->d_cov_delta;
     default: return nullptr;
   }
 }
@@ -1567,6 +1603,379 @@ int faucet_session_import_planes(faucet_session* s, int peer_rank, size_t n_text
 int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_recs) {
   if (!s->parsed) return fail(FAUCET_E_STATE, "no parsed batch");
   *n_text = s->n; *n_recs = s->n_recs;
+  return 0;
+}
+
+// ---- sharded epoch (shard.cuh): the stitch across GPUs ------------------------------------------------
+
+// the ordered executor over the records [begin, end) of the resident batch (stitch_batch = all of them, by epochs)
+int faucet_session_stitch_records(faucet_session* s, uint32_t begin, uint32_t end, int advance) {
+  if (!s->stitching) return fail(FAUCET_E_STATE, "stitch_begin not called");
+  if (!s->parsed) return fail(FAUCET_E_STATE, "stitch_records before parse");
+  if (begin > end || end > s->n_recs) return fail(FAUCET_E_ARG, "bad record range");
+  if (s->lpf.enabled()) return fail(FAUCET_E_STATE, "stitch_records does not feed the long pair filter: use stitch_batch");
+  int rc;
+  if (begin < end && (rc = stitch_run_flow(s, nullptr, begin, end, false, true, nullptr))) return rc;
+  s->ep.exact_epochs++; s->ep.exact_runs += end - begin;
+  if (advance) s->rec_base += s->n_recs;
+  return 0;
+}
+
+namespace {
+struct ShardInfo {  // what the ranks tell each other before a sharded epoch (FAUCET_SHARD_INFO_BYTES per rank)
+  uint64_t n_text, rec_base, tbl_cap;
+  uint32_t n_recs, r_begin, fastq, eligible;
+  StitchState st;
+};
+static_assert(sizeof(ShardInfo) <= FAUCET_SHARD_INFO_BYTES, "ShardInfo must fit its blob");
+
+// what every read-only kernel of the epoch gets: own planes, own replica, own count array / counter block
+void shard_args(faucet_session* s, StitchArgs& d) {
+  stitch_fill_args(s, d);
+  d.in_exact = s->d_in_exact; d.r_begin = s->shard.r_begin; d.r_end = s->n_recs;
+  d.dirty = s->d_dirty; d.dirty_max = s->d_dirty_max;
+  d.rows = s->d_rows; d.rows_base = s->shard.r_begin; d.recheck = 1; d.taint_mark = EX_COMMITTED;
+  d.st = s->d_st_quiet; d.special = &s->d_st->special;
+  d.cov_out = s->d_cov_delta; d.cov_stride = 4; d.cov_off = 0; d.cov_out2 = nullptr; d.st2 = nullptr;
+  d.rows_ready = s->rows_ahead && s->rows_ahead_n == s->n_recs && s->rows_ahead_begin == s->shard.r_begin ? 1 : 0;
+}
+void shard_dry(faucet_session* s, const StitchArgs& d, int mode, uint8_t want, uint8_t after, bool live) {
+  StitchArgs w = d;
+  w.dry_mode = mode; w.want_flag = want; w.flag_after = after;
+  if (!live) { w.keys = s->d_snap_keys; w.recs = s->d_snap_recs; w.special = &s->d_st_snap->special; }
+  KTimer kt(s, KT_DRY);
+  stitch_dry_kernel<<<g.sm_count * 8, DRY_THREADS, DRY_WARPS * sizeof(DryScratch), s->stream>>>(w);
+  s->launches++;
+}
+// the ascending list of this GPU's members of the exact set -> d_list; their number
+int shard_list(faucet_session* s, uint32_t* n_out) {
+  const uint32_t r = s->shard.r_begin, m = s->n_recs - r;
+  *n_out = 0;
+  if (!m) return 0;
+  const int grid = g.sm_count * 8;
+  const unsigned n_blocks = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  {
+    KTimer kt(s, KT_VERIFY);
+    exact_flags_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix);
+    scan_reduce_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
+    scan_sums_kernel<<<1, 1024, 0, s->stream>>>(s->d_eprefix_sums, n_blocks);
+    scan_apply_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
+    exact_list_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix, s->d_list, s->d_count);
+    s->launches += 5;
+  }
+  CU(cudaMemcpyAsync(n_out, s->d_count, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return check_launch("shard_list");
+}
+}  // namespace
+
+// Step 0 (every rank, after stitch_begin; the owner after its ordered prefix [0, r_begin)): what this rank brings to the
+// epoch.  The owner first makes room in its table for what the exact set may create (the table cannot grow while
+// replicas of it exist).  eligible = 0: this scan cannot be sharded (pair filters are fed): every rank must then take
+// the serial path.
+int faucet_session_shard_info(faucet_session* s, uint32_t r_begin, int is_owner, void* info_out) {
+  if (!s->stitching) return fail(FAUCET_E_STATE, "stitch_begin not called");
+  if (!s->parsed) return fail(FAUCET_E_STATE, "shard_info before parse");
+  if (r_begin > s->n_recs) return fail(FAUCET_E_ARG, "bad epoch start");
+  int rc;
+  ShardInfo in;
+  std::memset(&in, 0, sizeof in);
+  CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (is_owner) {
+    if ((rc = flow_init(s))) return rc;
+    // (the executor itself asks for n_entries + bound <= cap / 2 before every record; what is left above that is the room
+    // for the junctions the exact set may create -- if it runs out, the epoch is called off: shard_abort)
+    const unsigned long long bound = std::max<unsigned long long>(s->h_st.max_need, 1024) * (unsigned long long)s->flow_grid * STITCH_WARPS;
+    while (s->h_st.n_entries + s->h_st.n_entries / 8 + bound + 65536 > s->tbl_cap / 2)
+      if ((rc = stitch_grow_table(s))) return rc;
+  }
+  in.n_text = s->n; in.rec_base = s->rec_base; in.tbl_cap = s->tbl_cap; in.n_recs = s->n_recs; in.r_begin = r_begin;
+  in.fastq = s->fastq; in.eligible = (s->d_spf || s->lpf.enabled() || g.stitch_exec == 0) ? 0u : 1u;
+  in.st = s->h_st;
+  std::memset(info_out, 0, FAUCET_SHARD_INFO_BYTES);
+  std::memcpy(info_out, &in, sizeof in);
+  return 0;
+}
+
+// Optional, any time between parse and shard_begin: the reservation rows of this rank's records of the epoch (a pure
+// function of the text), e.g. while the owner is still busy with its prefix; classify then does not compute them.
+int faucet_session_shard_rows(faucet_session* s, uint32_t r_begin) {
+  if (!s->parsed) return fail(FAUCET_E_STATE, "shard_rows before parse");
+  if (r_begin > s->n_recs) return fail(FAUCET_E_ARG, "bad epoch start");
+  const uint32_t m = s->n_recs - r_begin;
+  s->rows_ahead = false;
+  if (!m) return 0;
+  int rc;
+  if ((size_t)m > s->rows_cap) {
+    cudaFree(s->d_rows); s->d_rows = nullptr;
+    s->rows_cap = (size_t)m + m / 4 + 1024;
+    if ((rc = dmalloc(&s->d_rows, s->rows_cap * ROW_WORDS))) return rc;
+  }
+  StitchArgs d;
+  stitch_fill_args(s, d);
+  d.rows = s->d_rows; d.rows_base = r_begin; d.r_begin = r_begin; d.r_end = s->n_recs;
+  {
+    KTimer kt(s, KT_FLOW_PREP);
+    stitch_rows_kernel<<<g.sm_count * 8, DRY_THREADS, 0, s->stream>>>(d);
+    s->launches++;
+  }
+  s->rows_ahead = true; s->rows_ahead_n = s->n_recs; s->rows_ahead_begin = r_begin;
+  return check_launch("shard_rows");
+}
+
+// Step 1: replicate T0 (ranks other than the owner), classify this rank's records of the epoch against it, snapshot, list
+// the exact set.  Needs the owner's FAUCET_BUF_TBL_KEYS / TBL_RECS / JSLOT opened after its shard_info call.
+int faucet_session_shard_begin(faucet_session* s, const void* infos, int n_ranks, int my_rank, int owner, uint32_t* n_exact_out) {
+  if (!s->peers_open || n_ranks != s->n_ranks || my_rank != s->rank) return fail(FAUCET_E_STATE, "peers not opened for this rank layout");
+  if (owner < 0 || owner >= n_ranks) return fail(FAUCET_E_ARG, "bad owner");
+  int rc;
+  ShardInfo in[MAX_PEERS];
+  for (int r = 0; r < n_ranks; r++) {
+    std::memcpy(&in[r], (const char*)infos + (size_t)r * FAUCET_SHARD_INFO_BYTES, sizeof(ShardInfo));
+    if (!in[r].eligible) return fail(FAUCET_E_STATE, "this scan cannot be sharded (pair filters / round executor)");
+  }
+  auto& sh = s->shard;
+  sh = faucet_session::Shard();
+  sh.owner = owner; sh.r_begin = in[my_rank].r_begin;
+  uint64_t base = in[0].rec_base;
+  for (int r = 0; r < n_ranks; r++) { sh.rec_base[r] = base; sh.n_recs[r] = in[r].n_recs; base += in[r].n_recs; }
+  sh.rec_base[n_ranks] = base;
+  if (base >= 0xfffffffeull) return fail(FAUCET_E_ARG, "sharded epoch: more than 2^32 - 2 records");
+  if (in[my_rank].n_recs != s->n_recs) return fail(FAUCET_E_STATE, "shard_begin: the resident batch changed since shard_info");
+  const unsigned long long cap = in[owner].tbl_cap;
+  if (my_rank != owner) {
+    if (s->tbl_cap != cap) {
+      cudaFree(s->d_keys); cudaFree(s->d_recs); cudaFree(s->d_jstamps);
+      s->d_keys = nullptr; s->d_recs = nullptr; s->d_jstamps = nullptr; s->tbl_cap = 0;
+      if ((rc = stitch_alloc_table(s, cap))) return rc;
+    }
+    const void *pk = s->peer[FAUCET_BUF_TBL_KEYS][owner], *pr = s->peer[FAUCET_BUF_TBL_RECS][owner], *pj = s->peer[FAUCET_BUF_JSLOT][owner];
+    if (!pk || !pr || !pj) return fail(FAUCET_E_STATE, "the owner's table is not opened");
+    {
+      KTimer kt(s, KT_SHARD_COPY);
+      CU(cudaMemcpyAsync(s->d_keys, pk, (cap + 1) * 8, cudaMemcpyDeviceToDevice, s->stream));
+      CU(cudaMemcpyAsync(s->d_recs, pr, (cap + 1) * REC_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream));
+      CU(cudaMemcpyAsync(s->d_jslot, pj, (((size_t)1 << g.res_log2) / 32 + 1) * 4, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    s->h_st = in[owner].st;
+    std::memset(s->h_st.stats, 0, sizeof s->h_st.stats);  // the counters of T0 live on the owner
+    s->h_st.ext_used = 0;
+    CU(cudaMemcpyAsync(s->d_st, &s->h_st, sizeof(StitchState), cudaMemcpyHostToDevice, s->stream));
+  } else if (s->tbl_cap != cap) {
+    return fail(FAUCET_E_STATE, "shard_begin: the owner's table changed since shard_info");
+  }
+  s->rec_base = sh.rec_base[my_rank];
+  const uint32_t m = s->n_recs - sh.r_begin;
+  if ((rc = stitch_ensure_epoch_buffers(s, std::max<uint32_t>(m, 1)))) return rc;
+  if (s->cov_delta_cap != cap) {
+    cudaFree(s->d_cov_delta); s->d_cov_delta = nullptr; s->cov_delta_cap = 0;
+    if ((rc = dmalloc(&s->d_cov_delta, (cap + 1) * 4))) return rc;
+    s->cov_delta_cap = cap;
+  }
+  if (!s->d_st_quiet && (rc = dmalloc(&s->d_st_quiet, 1))) return rc;
+  CU(cudaMemsetAsync(s->d_cov_delta, 0, (cap + 1) * 16, s->stream));
+  CU(cudaMemsetAsync(s->d_st_quiet, 0, sizeof(StitchState), s->stream));
+  CU(cudaMemsetAsync(s->d_in_exact, 0, s->n_recs ? s->n_recs : 1, s->stream));
+  sh.active = true;
+  if (m) {
+    StitchArgs d;
+    shard_args(s, d);
+    shard_dry(s, d, DRY_CLASSIFY_APPLY, 0, 0, true);
+  }
+  if ((rc = stitch_snapshot(s))) return rc;
+  sh.snapshot = true;
+  s->ep.classify_epochs++; s->ep.dry_records += m;
+  if ((rc = shard_list(s, n_exact_out))) return rc;
+  s->ep.nonquiet += *n_exact_out;
+  return 0;
+}
+
+// Step 2: the whole exact set -- n_exact[r] entries of rank r's list, r = 0 .. n_ranks-1, in that order -- through the
+// ordered executor on this rank's replica (restored to T0 first when iter > 0).  The lines of all members are gathered
+// into one small local batch first (shard.cuh).  *need_grow_out: the table would have to grow; every rank must then call
+// shard_abort and the job falls back to the serial path.
+int faucet_session_shard_execute(faucet_session* s, const uint32_t* n_exact, int iter, int* need_grow_out) {
+  auto& sh = s->shard;
+  if (!sh.active) return fail(FAUCET_E_STATE, "no sharded epoch is open");
+  *need_grow_out = 0;
+  int rc;
+  if (iter > 0 && (rc = stitch_restore(s, 0))) return rc;
+  CU(cudaMemsetAsync(s->d_dirty, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
+  CU(cudaMemsetAsync(s->d_dirty_max, 0, ((size_t)1 << g.res_log2) * 4, s->stream));
+  if (g.shard_force_abort && iter == 0) { *need_grow_out = 1; return 0; }
+  sh.ran = true;
+  GatherArgs ga;
+  std::memset(&ga, 0, sizeof ga);
+  ga.n_ranks = s->n_ranks;
+  uint64_t n_total = 0;
+  for (int r = 0; r < s->n_ranks; r++) {
+    const bool me = r == s->rank;
+    ga.first[r] = (uint32_t)n_total;
+    n_total += n_exact[r];
+    ga.rec_base[r] = (uint32_t)sh.rec_base[r];
+    ga.inval[r] = me ? s->d_inval : (const uint32_t*)s->peer[FAUCET_BUF_INVAL][r];
+    ga.packed[r] = me ? s->d_packed : (const uint32_t*)s->peer[FAUCET_BUF_PACKED][r];
+    ga.flags[r] = me ? s->d_flags : (const uint8_t*)s->peer[FAUCET_BUF_FLAGS][r];
+    ga.seq_start[r] = me ? s->d_seq_start : (const uint32_t*)s->peer[FAUCET_BUF_SEQ_START][r];
+    ga.seq_end[r] = me ? s->d_seq_end : (const uint32_t*)s->peer[FAUCET_BUF_SEQ_END][r];
+    ga.list[r] = me ? s->d_list : (const uint32_t*)s->peer[FAUCET_BUF_EXACT_LIST][r];
+    if (n_exact[r] && (!ga.list[r] || !ga.packed[r] || !ga.inval[r] || !ga.flags[r] || !ga.seq_start[r] || !ga.seq_end[r]))
+      return fail(FAUCET_E_STATE, "a peer's exact list / planes are not opened");
+  }
+  ga.first[s->n_ranks] = (uint32_t)n_total;
+  if (n_total >= (1ull << 31)) return fail(FAUCET_E_ARG, "exact set too large");
+  const uint32_t n = (uint32_t)n_total;
+  ga.n = n;
+  if (!n) { s->ep.iterations++; return 0; }
+  if (n > s->mb_entries_cap) {
+    cudaFree(s->mb_seq_start); cudaFree(s->mb_seq_end); cudaFree(s->mb_gid); cudaFree(s->mb_span); cudaFree(s->mb_span_sums);
+    s->mb_seq_start = s->mb_seq_end = s->mb_gid = s->mb_span = s->mb_span_sums = nullptr;
+    s->mb_entries_cap = (size_t)n + n / 2 + 4096;
+    if ((rc = dmalloc(&s->mb_seq_start, s->mb_entries_cap)) || (rc = dmalloc(&s->mb_seq_end, s->mb_entries_cap)) ||
+        (rc = dmalloc(&s->mb_gid, s->mb_entries_cap)) || (rc = dmalloc(&s->mb_span, s->mb_entries_cap + 1)) ||
+        (rc = dmalloc(&s->mb_span_sums, s->mb_entries_cap / SCAN_CHUNK + 4)))
+      return rc;
+  }
+  ga.span = s->mb_span; ga.o_seq_start = s->mb_seq_start; ga.o_seq_end = s->mb_seq_end; ga.o_gid = s->mb_gid;
+  uint32_t tail[2] = {0, 0};
+  const int grid = (int)std::min<uint64_t>((uint64_t)g.sm_count * 8, (n + 7) / 8);
+  {
+    KTimer kt(s, KT_SHARD_COPY);
+    shard_gather_spans_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(ga);
+    CU(cudaMemcpyAsync(&tail[0], s->mb_span + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+    exclusive_scan_u32(s, s->mb_span, n, s->mb_span_sums);
+    CU(cudaMemcpyAsync(&tail[1], s->mb_span + n - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+    s->launches++;
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  if ((rc = check_launch("shard_gather_spans"))) return rc;
+  const uint64_t total = (uint64_t)tail[0] + tail[1];
+  if (total >= (3ull << 30)) return fail(FAUCET_E_ARG, "exact set too large for one gathered batch");
+  if (total + 4096 > s->mb_pos_cap) {
+    cudaFree(s->mb_inval); cudaFree(s->mb_packed); cudaFree(s->mb_flags);
+    s->mb_inval = s->mb_packed = nullptr; s->mb_flags = nullptr;
+    s->mb_pos_cap = total + total / 2 + 65536;
+    if ((rc = dmalloc(&s->mb_inval, s->mb_pos_cap / 32 + 64)) || (rc = dmalloc(&s->mb_packed, s->mb_pos_cap / 16 + 64)) ||
+        (rc = dmalloc(&s->mb_flags, s->mb_pos_cap + 64)))
+      return rc;
+  }
+  ga.o_inval = s->mb_inval; ga.o_packed = s->mb_packed; ga.o_flags = s->mb_flags;
+  {
+    KTimer kt(s, KT_SHARD_COPY);
+    shard_gather_copy_kernel<<<grid, 256, 0, s->stream>>>(ga, (uint32_t)total);
+    s->launches++;
+  }
+  // the executor runs the gathered batch as if it were the resident one
+  struct Planes { uint32_t *inval, *packed, *seq_start, *seq_end; uint8_t* flags; uint32_t n_recs; uint64_t rec_base; } own =
+      {s->d_inval, s->d_packed, s->d_seq_start, s->d_seq_end, s->d_flags, s->n_recs, s->rec_base};
+  s->d_inval = s->mb_inval; s->d_packed = s->mb_packed; s->d_flags = s->mb_flags; s->d_seq_start = s->mb_seq_start; s->d_seq_end = s->mb_seq_end;
+  s->n_recs = n; s->rec_base = 0; s->cur_gid = s->mb_gid; s->prep_valid = false;
+  bool need_grow = false;
+  rc = stitch_run_flow(s, nullptr, 0, n, true, false, &need_grow);
+  s->d_inval = own.inval; s->d_packed = own.packed; s->d_seq_start = own.seq_start; s->d_seq_end = own.seq_end; s->d_flags = own.flags;
+  s->n_recs = own.n_recs; s->rec_base = own.rec_base; s->cur_gid = nullptr; s->prep_valid = false;
+  if (rc) return rc;
+  s->ep.exact_runs += n;
+  if (need_grow) { *need_grow_out = 1; return 0; }
+  s->ep.iterations++;
+  return 0;
+}
+
+// Step 3: which of this rank's quiet records may have seen something else than T0 (verify), the second look of those
+// with earlier writes only (recheck), the commits of the ones that join the exact set taken back (retract); the new list.
+int faucet_session_shard_verify(faucet_session* s, uint32_t* n_exact_out) {
+  auto& sh = s->shard;
+  if (!sh.active) return fail(FAUCET_E_STATE, "no sharded epoch is open");
+  if (s->n_recs > sh.r_begin) {
+    StitchArgs d;
+    shard_args(s, d);
+    {
+      KTimer kt(s, KT_VERIFY);
+      stitch_verify_kernel<<<g.sm_count * 8, DRY_THREADS, 0, s->stream>>>(d);
+      s->launches++;
+    }
+    shard_dry(s, d, DRY_RECHECK, EX_RECHECK, 0, true);
+    shard_dry(s, d, DRY_RETRACT, EX_COMMITTED, EX_RETRACTED, false);
+  }
+  return shard_list(s, n_exact_out);
+}
+
+// Step 4: the settled records (they saw the replica as the last exact run left it) move their commit from the walk on T0
+// to the walk on that table; this rank's counters of the epoch -> stats_out (FAUCET_SHARD_STATS entries).
+int faucet_session_shard_finish(faucet_session* s, uint64_t* stats_out) {
+  auto& sh = s->shard;
+  if (!sh.active) return fail(FAUCET_E_STATE, "no sharded epoch is open");
+  if (sh.ran && s->n_recs > sh.r_begin) {
+    StitchArgs d;
+    shard_args(s, d);
+    shard_dry(s, d, DRY_RETRACT, EX_SETTLED, EX_SETTLED, false);
+    shard_dry(s, d, DRY_APPLY, EX_SETTLED, 0, true);
+  }
+  StitchState q;
+  CU(cudaMemcpyAsync(&q, s->d_st_quiet, sizeof q, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  int rc = check_launch("shard_finish");
+  if (rc) return rc;
+  if (q.stats[SS_DRY_ERROR]) return fail(FAUCET_E_CUDA, "sharded epoch: apply met a record that is not quiet (internal error)");
+  static_assert(FAUCET_SHARD_STATS >= SS_COUNT, "stats blob too small");
+  for (int i = 0; i < FAUCET_SHARD_STATS; i++) stats_out[i] = i < SS_COUNT ? q.stats[i] : 0;
+  return 0;
+}
+
+// Step 5 (owner; after a barrier): the count arrays of all ranks into the owner's table, their counters into its
+// counter block.  stats_all: n_ranks x FAUCET_SHARD_STATS, what shard_finish returned on every rank.
+int faucet_session_shard_merge(faucet_session* s, const uint64_t* stats_all) {
+  auto& sh = s->shard;
+  if (!sh.active) return fail(FAUCET_E_STATE, "no sharded epoch is open");
+  if (s->rank != sh.owner) return fail(FAUCET_E_STATE, "shard_merge runs on the owner of the table");
+  StitchArgs a;
+  stitch_fill_args(s, a);
+  {
+    KTimer kt(s, KT_SHARD_MERGE);
+    for (int r = 0; r < s->n_ranks; r++) {
+      const unsigned long long* pk = r == s->rank ? s->d_keys : (const unsigned long long*)s->peer[FAUCET_BUF_TBL_KEYS][r];
+      const uint4* pc = r == s->rank ? (const uint4*)s->d_cov_delta : (const uint4*)s->peer[FAUCET_BUF_COV_DELTA][r];
+      if (!pk || !pc) return fail(FAUCET_E_STATE, "a peer's table / count array is not opened");
+      shard_merge_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(pk, pc, s->tbl_cap, a, r == s->rank ? 1 : 0);
+      s->launches++;
+    }
+  }
+  unsigned long long add[SS_COUNT] = {0};
+  for (int r = 0; r < s->n_ranks; r++)
+    for (int i = 0; i < SS_WALK; i++) add[i] += stats_all[(size_t)r * FAUCET_SHARD_STATS + i];
+  CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  int rc = check_launch("shard_merge");
+  if (rc) return rc;
+  if (s->h_st.stats[SS_DRY_ERROR]) return fail(FAUCET_E_CUDA, "sharded epoch: a peer counted coverage on a junction the owner does not hold (internal error)");
+  for (int i = 0; i < SS_WALK; i++) s->h_st.stats[i] += add[i];
+  CU(cudaMemcpyAsync(s->d_st->stats, s->h_st.stats, sizeof(unsigned long long) * SS_WALK, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->rec_base = sh.rec_base[s->n_ranks];  // the whole stream is in the map now
+  sh.active = false;
+  return 0;
+}
+
+// closes the epoch on a rank that does not merge (every rank but the owner)
+int faucet_session_shard_end(faucet_session* s) {
+  s->shard.active = false;
+  return 0;
+}
+
+// The epoch is called off (the table would have to grow): the replica goes back to T0 and the commits of the epoch are
+// forgotten; the owner then runs its records [r_begin, n_recs) and the other shards through the serial path.
+int faucet_session_shard_abort(faucet_session* s) {
+  auto& sh = s->shard;
+  if (!sh.active) return 0;
+  int rc;
+  if (sh.snapshot && (rc = stitch_restore(s, 0))) return rc;
+  CU(cudaMemcpyAsync(&s->h_st, s->d_st, sizeof(StitchState), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->rec_base = sh.rec_base[s->rank];
+  sh.active = false;
+  s->ep.fallbacks++;
   return 0;
 }
 

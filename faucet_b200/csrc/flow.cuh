@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_flow_kernel
   WarpCtx c;
   if (lane < SS_COUNT) S->st[lane] = 0;
   __syncwarp();
-  c.S = S; c.stage = S->stage; c.cnt = S->st; c.n_stage = 0; c.part = 0; c.stamp = 0; c.n_vis = 0; c.wrote = false;
+  c.S = S; c.stage = S->stage; c.cnt = S->st; c.n_stage = 0; c.part = 0; c.stamp = 0; c.n_vis = 0; c.wrote = false; c.grec = 0;
   c.land_slot = nullptr; c.land_nt = nullptr; c.n_land = 0; c.emit = true;
   __shared__ unsigned long long pool;  // {end : 32 | next : 32} of the CTA's drawn tickets
   if (threadIdx.x == 0) pool = 0ull;
@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_flow_kernel
     if (__ldcg(&st->status) != ST_DONE) continue;
     __syncwarp();
     c.rec = rec; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls; c.wrote = false;
-    c.stamp = (a.rec_base + rec) << STAMP_SHIFT;
+    c.grec = global_rec(a, rec);
+    c.stamp = global_stamp(a, rec);
     if (fast) {
       if (lane < (int)n_row) S->reskey[lane] = __ldg(f.rows + (size_t)i * ROW_WORDS + 1 + lane);
       __syncwarp();

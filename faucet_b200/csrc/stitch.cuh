@@ -128,7 +128,8 @@ struct StitchArgs {
   const uint32_t* seq_end;
   uint32_t n_recs;               // ordered kernel: it runs the entries [st->next, n_recs) ...
   const uint32_t* list;          // ... of this ascending list of record indices (NULL: the record indices themselves)
-  unsigned long long rec_base;   // global index of record 0 of this batch
+  unsigned long long rec_base;   // global index of record 0 of this batch ...
+  const uint32_t* gid;           // ... or, per record of the batch, its global index (the gathered exact set of a sharded epoch)
   int k, j, spacer;
   int no_cleaning, paired;
   unsigned long long* keys;      // cap + 1 entries (the last one is the home of the KEY_EMPTY k-mer)
@@ -144,6 +145,8 @@ struct StitchArgs {
   uint32_t* dirty_max;           // ... and 1 + the largest such index
   // read-only walk (stitch_dry_kernel / stitch_verify_kernel): keys/recs above are the epoch's T0 snapshot
   uint32_t* cov_out;             // records of the LIVE table: apply adds the coverage counts here (same slots as T0)
+  uint32_t cov_stride, cov_off;  // ... laid out as cov_out[slot * cov_stride + cov_off + nt]: the records themselves
+                                 // (REC_WORDS, REC_COV) or a shard's own count array (4, 0; sharded epochs, multi.cuh)
   uint32_t* cov_out2;            // retract: the snapshot's records too (a later restore must not bring the counts back)
   StitchState* st2;              // retract: the snapshot's counters too
   uint8_t* in_exact;             // per record of the batch: 0 = quiet (applied, if classify applies), 1 = exact set (never
@@ -151,6 +154,8 @@ struct StitchArgs {
   uint8_t taint_mark;            // what joins the exact set after classify gets: EX_MEMBER, or EX_COMMITTED when classify applied
   uint8_t want_flag, flag_after; // apply / retract / recheck take the records with in_exact == want_flag; retract leaves flag_after
   uint8_t recheck;               // verify: records with earlier but no later writes are rechecked on the live table (else they join)
+  uint8_t lazy;                  // read-only walk: look keys up as the walk reaches them instead of parking the whole line first
+  uint8_t rows_ready;            // classify: a.rows already holds the reservation rows (stitch_rows_kernel ran ahead)
   uint32_t* rows;                // classify writes, verify and the later walks read: ROW_WORDS u32 per record of the epoch
   uint32_t rows_base;            // record of row 0
   uint32_t r_begin, r_end;       // the epoch
@@ -370,6 +375,13 @@ __device__ void spf_add_pair(const StitchArgs& a, uint64_t k1, uint64_t k2) {
   }
 }
 
+__device__ __forceinline__ uint32_t global_rec(const StitchArgs& a, uint32_t rec) {
+  return a.gid ? __ldg(a.gid + rec) : (uint32_t)a.rec_base + rec;
+}
+__device__ __forceinline__ unsigned long long global_stamp(const StitchArgs& a, uint32_t rec) {
+  return (a.gid ? (unsigned long long)__ldg(a.gid + rec) : a.rec_base + rec) << STAMP_SHIFT;
+}
+
 struct WarpCtx {
   unsigned long long stamp;         // next creation stamp of the current record
   WarpScratch* S;                   // lookups parked by phase 1 (ordered kernel, lines that fit POS_CAP)
@@ -384,6 +396,7 @@ struct WarpCtx {
   int n_pos;                        // k-mer positions of the line held in S (0: direct path)
   int n_vis;                        // entries of S->visited (> VIS_CAP: overflowed)
   uint32_t n_stage, part, rec;
+  uint32_t grec;                    // global index of the record (creation stamps, epoch marks)
   bool wrote;                       // ordered kernel: the record changed something a later record can see, or set a link
   // read-only walk
   uint32_t* land_slot;              // junction slots the line landed on ...
@@ -461,7 +474,8 @@ __device__ __forceinline__ void line_publish(const StitchArgs& a, WarpCtx& c, ui
   __syncwarp();
 }
 // epoch bookkeeping of the ordered kernel: a junction with this key was created or had a distance raised by `rec`
-// (and `created`: the slot now holds a junction)
+// (and `created`: the slot now holds a junction).  `rec` is the GLOBAL record index (u32: a scan of < 2^32 - 2 records):
+// the exact set of a sharded epoch spans the shards of several GPUs.
 __device__ __forceinline__ void mark_written(const StitchArgs& a, uint64_t key, uint32_t rec, bool created, bool visible, int lane) {
   if (!created && !(visible && a.dirty)) return;
   const uint32_t slot = kmer_res_slot(key, a.k, a.res_mask, lane);
@@ -629,8 +643,8 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
     line_visit(c, slot, lane);
     if (wr) {
       c.wrote = true;
-      mark_written(a, key, c.rec, created, (wr & 1u) != 0, lane);
-      mark_written(a, last_key, c.rec, false, (wr & 2u) != 0, lane);
+      mark_written(a, key, c.grec, created, (wr & 1u) != 0, lane);
+      mark_written(a, last_key, c.grec, false, (wr & 2u) != 0, lane);
     }
     if (pairs || want_ext) out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), dir, pos, pairs, want_ext, lane);
     have_last = true;
@@ -665,7 +679,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       c.stamp = __shfl_sync(0xffffffffu, c.stamp, 0);
       wr = __shfl_sync(0xffffffffu, wr, 0);
     }
-    if (wr) { c.wrote = true; mark_written(a, key, c.rec, created, true, lane); }
+    if (wr) { c.wrote = true; mark_written(a, key, c.grec, created, true, lane); }
     if (FAST && created) line_publish(a, c, key, slot, lane);
     line_visit(c, slot, lane);
     if (pairs || want_ext) out_push(a, c, o, ext_fwd(key, (uint32_t)real, mask), -1, pos, pairs, want_ext, lane);
@@ -678,7 +692,7 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
       if (lane == 0) wr = atomicMax(rec_field(a, last_slot, REC_DIST + last_fwd_idx), dv) < dv;
       wr = __shfl_sync(0xffffffffu, wr, 0);
     }
-    if (wr) { c.wrote = true; mark_written(a, last_key, c.rec, false, true, lane); }
+    if (wr) { c.wrote = true; mark_written(a, last_key, c.grec, false, true, lane); }
   }
   if (lane == 0) { c.cnt[SS_JCHECK] += n_jcheck; c.cnt[SS_PROCESSED] += n_processed; c.cnt[SS_SKIPPED] += n_skipped; }
   __syncwarp();
@@ -690,7 +704,8 @@ __device__ void scan_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int l
 // sub-read leaves its landings in c.land_* (coverage counts, added when the record commits), its counters in c.cnt
 // and, when c.emit, its pair-filter / extension-list side effects.
 // FAST: slots, distances and link masks of every half-step of the line were parked in c.S by prefetch_line.
-template <bool FAST>
+// LAZY (with FAST planes): junction keys and records are looked up as the walk reaches them.
+template <bool FAST, bool LAZY = false>
 __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int len, int lane) {
   const int k = a.k, j = a.j;
   const uint64_t mask = kmer_mask(k);
@@ -725,8 +740,12 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
       if (active) {
         const int pos = t >> 1, dir = t & 1;
         uint32_t f;
-        if (FAST) {
+        if (FAST && !LAZY) {
           sl = c.S->slot[2 * (rel + pos) + dir];
+          f = c.S->flag[rel + pos];
+        } else if (FAST) {
+          const uint64_t fwd = line_kmer(a, c, rel + pos);
+          sl = tbl_find(a, dir ? fwd : revcomp(fwd, k));
           f = c.S->flag[rel + pos];
         } else {
           const uint64_t fwd = kmer_at_t<false>(a.packed, s0 + pos, k);
@@ -762,7 +781,7 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
                          : (int)nt_comp(code_at_t<FAST>(c.pk, s0 + pos - 1 - c.pk_base));
     const int fwd_idx = dir ? real : 4, back_idx = dir ? 4 : real;
     uint32_t d_fwd, d_back, link;
-    if (FAST) {
+    if (FAST && !LAZY) {
       const int hs = 2 * (rel + pos) + dir;
       d_fwd = c.S->hop[hs]; d_back = c.S->dback[hs]; link = c.S->lnk[hs];
     } else {
@@ -793,7 +812,7 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
     const int real = (int)code_at_t<FAST>(c.pk, s0 + pos + k - c.pk_base);
     int slot;
     uint32_t have4, have_real;  // its dist[4] and dist[real]
-    if (FAST) {
+    if (FAST && !LAZY) {
       const int hs = 2 * (rel + pos) + 1;
       slot = c.S->slot[hs]; have4 = c.S->dback[hs]; have_real = c.S->hop[hs];
     } else {
@@ -836,7 +855,7 @@ __device__ long long find_prev_bit(const uint32_t* plane, uint32_t s, uint32_t p
 
 // scanInputRead (:260-282) + getValidReads (:233-257) for the sequence line [ls, le).
 // DRY: the read-only walk; returns false when the line is not quiet (always true otherwise).
-template <bool FAST, bool DRY>
+template <bool FAST, bool DRY, bool LAZY = false>
 __device__ bool scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t le, int lane) {
   const int k = a.k, j = a.j;
   uint32_t pos = le;
@@ -872,7 +891,7 @@ __device__ bool scan_line(const StitchArgs& a, WarpCtx& c, uint32_t ls, uint32_t
           bit += __ffs(x) - 1;
           const int run_len = base + bit - run_start;
           if (run_len >= k) {
-            if (DRY) { if (!dry_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane)) return false; }
+            if (DRY) { if (!dry_forward<FAST, LAZY>(a, c, ss + run_start, run_len + k - 1, lane)) return false; }
             else scan_forward<FAST>(a, c, ss + run_start, run_len + k - 1, lane);
             if (lane == 0) c.cnt[SS_NOERR]++;
           }
@@ -993,7 +1012,7 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
   if (lane < SS_COUNT) S->st[lane] = 0;
   __syncwarp();
   c.S = S; c.stage = S->stage; c.cnt = S->st; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0; c.n_stage = 0; c.part = 0;
-  c.rec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0; c.wrote = false;
+  c.rec = 0; c.grec = 0; c.stamp = 0; c.ls = 0; c.n_pos = 0; c.n_vis = 0; c.wrote = false;
   c.land_slot = nullptr; c.land_nt = nullptr; c.n_land = 0; c.emit = true;
   uint32_t status = ST_DONE;
 
@@ -1063,7 +1082,8 @@ __global__ void __launch_bounds__(STITCH_THREADS, MIN_BLOCKS) stitch_kernel(Stit
       if (gw == 0 && lane == 0) S->st[SS_T_P2A] += gtime_ns() - t2;
       if (mine) {
         c.rec = rec; c.part = 0; c.n_stage = 0; c.n_vis = 0; c.ls = ls; c.wrote = false;
-        c.stamp = (a.rec_base + rec) << STAMP_SHIFT;
+        c.grec = global_rec(a, rec);
+        c.stamp = global_stamp(a, rec);
         if (fast) {
           c.n_pos = (int)(len - a.k + 1);
           c.pk = S->pk; c.pk_base = ls & ~15u; c.inv = S->inv; c.inv_base = ls & ~31u;
@@ -1131,14 +1151,18 @@ __global__ void __launch_bounds__(DRY_THREADS, 3) stitch_dry_kernel(StitchArgs a
   c.emit = a.dry_mode == DRY_APPLY;
   const int mode = a.dry_mode;
   const bool classify = mode == DRY_CLASSIFY || mode == DRY_CLASSIFY_APPLY;
-  for (uint32_t rec = a.r_begin + gw; rec < a.r_end; rec += n_warps) {
-    if (!classify && a.in_exact[rec] != a.want_flag) continue;
+  // 32 consecutive records per warp and step: the lanes read the flags, the warp then takes the wanted records in turn
+  for (uint32_t base = a.r_begin + gw * 32u; base < a.r_end; base += n_warps * 32u) {
+   uint32_t todo = __ballot_sync(0xffffffffu, base + lane < a.r_end && (classify || a.in_exact[base + lane] == a.want_flag));
+   while (todo) {
+    const uint32_t rec = base + (uint32_t)(__ffs(todo) - 1);
+    todo &= todo - 1u;
     const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
     const uint32_t len = le > ls ? le - ls : 0u;
     const int n_pos = len >= (uint32_t)a.k ? (int)(len - a.k + 1) : 0;
     const bool fast = n_pos > 0 && n_pos <= POS_CAP;
-    uint32_t* row = classify ? a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS : nullptr;
-    c.rec = rec; c.part = 0; c.n_stage = 0; c.n_land = 0; c.ls = ls;
+    uint32_t* row = classify && !a.rows_ready ? a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS : nullptr;
+    c.rec = rec; c.grec = 0; c.part = 0; c.n_stage = 0; c.n_land = 0; c.ls = ls;
     if (lane < SS_WALK) S->cnt[lane] = 0;
     bool quiet = true;
     if (fast) {
@@ -1147,22 +1171,26 @@ __global__ void __launch_bounds__(DRY_THREADS, 3) stitch_dry_kernel(StitchArgs a
       for (int pos = lane; pos < n_pos; pos += 32) W->flag[pos] = a.flags[ls + pos];
       __syncwarp();
       int n_res = 0;
-      if (classify) {
+      if (row) {
         line_reservations<3, true>(a, W->pk, ls & 15u, len, rec, lane, W->reskey, &n_res, ROW_WORDS - 1);
         __syncwarp();
         if (lane == 0) row[0] = n_res < ROW_WORDS ? (uint32_t)n_res : 255u;
         if (lane + 1 < ROW_WORDS && lane < n_res) row[1 + lane] = W->reskey[lane];
-      } else {  // the row classify left
+      } else if (!a.lazy) {  // the row classify (or stitch_rows_kernel) left
         const uint32_t* rr = a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS;
         n_res = (int)__ldg(rr);
         if (lane + 1 < ROW_WORDS && lane < n_res) W->reskey[lane] = __ldg(rr + 1 + lane);
         __syncwarp();
       }
-      prefetch_line<2>(a, W, ls, n_pos, lane, n_res < ROW_WORDS ? n_res : -1);
       c.n_pos = n_pos; c.pk = W->pk; c.pk_base = ls & ~15u; c.inv = W->inv; c.inv_base = ls & ~31u;
-      quiet = scan_line<true, true>(a, c, ls, le, lane);
+      if (a.lazy) {
+        quiet = scan_line<true, true, true>(a, c, ls, le, lane);
+      } else {
+        prefetch_line<2>(a, W, ls, n_pos, lane, n_res < ROW_WORDS ? n_res : -1);
+        quiet = scan_line<true, true>(a, c, ls, le, lane);
+      }
     } else {
-      if (classify && lane == 0) row[0] = len ? 255u : 0u;
+      if (row && lane == 0) row[0] = len ? 255u : 0u;
       if (len) {
         __syncwarp();
         c.n_pos = 0; c.pk = a.packed; c.pk_base = 0; c.inv = a.inval; c.inv_base = 0;
@@ -1183,18 +1211,43 @@ __global__ void __launch_bounds__(DRY_THREADS, 3) stitch_dry_kernel(StitchArgs a
     if (mode == DRY_CLASSIFY) continue;
     const uint32_t one = mode == DRY_RETRACT ? 0xffffffffu : 1u;
     for (int i = lane; i < c.n_land; i += 32) {
-      const size_t w = (size_t)S->land_slot[i] * REC_WORDS + REC_COV + S->land_nt[i];
-      atomicAdd(a.cov_out + w, one);
-      if (mode == DRY_RETRACT && a.cov_out2) atomicAdd(a.cov_out2 + w, one);
+      atomicAdd(a.cov_out + (size_t)S->land_slot[i] * a.cov_stride + a.cov_off + S->land_nt[i], one);
+      if (mode == DRY_RETRACT && a.cov_out2) atomicAdd(a.cov_out2 + (size_t)S->land_slot[i] * REC_WORDS + REC_COV + S->land_nt[i], one);
     }
     if (lane < SS_WALK) { if (mode == DRY_RETRACT) W->st[lane] -= S->cnt[lane]; else W->st[lane] += S->cnt[lane]; }
     if (mode == DRY_RETRACT && lane == 0) a.in_exact[rec] = a.flag_after;
     if (a.ext && c.n_stage) ext_flush(a, c, lane);
+   }
   }
   __syncwarp();
   if (lane < SS_COUNT && W->st[lane]) {
     atomicAdd(&a.st->stats[lane], W->st[lane]);
     if (mode == DRY_RETRACT && a.st2) atomicAdd(&a.st2->stats[lane], W->st[lane]);
+  }
+}
+
+// The reservation rows of the records [r_begin, r_end) -- what classify would write -- ahead of the epoch: a pure
+// function of the text (a GPU that waits for the table of a sharded epoch has time for it).
+__global__ void __launch_bounds__(DRY_THREADS) stitch_rows_kernel(StitchArgs a) {
+  __shared__ uint32_t keep_s[DRY_WARPS][ROW_WORDS];
+  uint32_t* keep = keep_s[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * DRY_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * DRY_THREADS) >> 5;
+  for (uint32_t rec = a.r_begin + gw; rec < a.r_end; rec += n_warps) {
+    const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
+    const uint32_t len = le > ls ? le - ls : 0u;
+    const int n_pos = len >= (uint32_t)a.k ? (int)(len - a.k + 1) : 0;
+    uint32_t* row = a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS;
+    int n = 0;
+    if (n_pos > 0 && n_pos <= POS_CAP) {
+      line_reservations<3, false>(a, a.packed, ls, len, rec, lane, keep, &n, ROW_WORDS - 1);
+      __syncwarp();
+      if (lane == 0) row[0] = n < ROW_WORDS ? (uint32_t)n : 255u;
+      if (lane + 1 < ROW_WORDS && lane < n) row[1 + lane] = keep[lane];
+    } else if (lane == 0) {
+      row[0] = len ? 255u : 0u;
+    }
+    __syncwarp();
   }
 }
 
@@ -1216,12 +1269,13 @@ __global__ void __launch_bounds__(DRY_THREADS) stitch_verify_kernel(StitchArgs a
     if (fl != EX_QUIET && fl != EX_SETTLED) continue;
     const uint32_t* row = a.rows + (size_t)(rec - a.rows_base) * ROW_WORDS;
     const uint32_t n_row = __ldg(row);
+    const uint32_t grec = (uint32_t)a.rec_base + rec;  // the marks hold global record indices
     bool before = false, after = false;
     if (n_row < ROW_WORDS) {
       if (lane < (int)n_row) {
         const uint32_t sl = __ldg(row + 1 + lane) & ROW_SLOT_MASK;
-        before = __ldcg(a.dirty + sl) < rec;
-        after = __ldcg(a.dirty_max + sl) > rec + 1u;
+        before = __ldcg(a.dirty + sl) < grec;
+        after = __ldcg(a.dirty_max + sl) > grec + 1u;
       }
     } else {  // more slots than a row holds: list them again
       const uint32_t ls = __ldg(a.seq_start + rec), le = __ldg(a.seq_end + rec);
@@ -1230,8 +1284,8 @@ __global__ void __launch_bounds__(DRY_THREADS) stitch_verify_kernel(StitchArgs a
       __syncwarp();
       if (n > RES_CAP) before = after = true;  // (and more than fit here: the ordered kernel takes the line)
       for (int i = lane; i < n && i < RES_CAP; i += 32) {
-        before |= __ldcg(a.dirty + (keep[i] & ROW_SLOT_MASK)) < rec;
-        after |= __ldcg(a.dirty_max + (keep[i] & ROW_SLOT_MASK)) > rec + 1u;
+        before |= __ldcg(a.dirty + (keep[i] & ROW_SLOT_MASK)) < grec;
+        after |= __ldcg(a.dirty_max + (keep[i] & ROW_SLOT_MASK)) > grec + 1u;
       }
       __syncwarp();
     }

@@ -146,7 +146,9 @@ int faucet_gpu_get_timings(faucet_timings* out);
  *           two, grows by rehash at load 1/2); "res_log2" log2 of the reservation-table entries; "stitch_w0" /
  *           "stitch_w_max" initial / maximal records per round; "stitch_shrink_den" / "stitch_grow_den" window
  *           adaptation; "stitch_blocks" resident CTAs per SM (2..4); "ext_cap0" u64 words of the extension-list buffer
- *           that feeds the long pair filter
+ *           that feeds the long pair filter; "shard_force_abort" 1 = a sharded epoch's first exact run reports that the
+ *           table must grow (tests of the fallback to the serial path); "dry_lazy" 1 = the read-only walks of the epochs look
+ *           junction keys up as they reach them (default), 0 = they park the lookups of the whole line first
  *  scan:    "scan_memo" 1 = scan_flags caches the extension masks of every k-mer it has computed (default), 0 = every
  *           position from the Bloom filter; "memo_shift" cache entries = Bloom bits >> memo_shift (8 bytes each)
  *  load:    "load_sub_bytes0" / "load_sub_bytes" first / largest sub-batch of pass 1; "load_memo_log2" pass 1 caches
@@ -195,7 +197,8 @@ int faucet_session_timer_stop_ms(faucet_session* s, float* ms_out);
 uint64_t faucet_session_kernel_launches(faucet_session* s);
 /* event-timed duration (ms) accumulated per named kernel since the last reset:
  * 0=parse 1=load_A 2=load_B 3=scan_flags 4=stitch (ordered kernel) 5=stitch_dry (read-only walks) 6=stitch_verify (verify + exact-set list)
- * 7=stitch_flow_prep (dependency sort of the dataflow executor) */
+ * 7=stitch_flow_prep (dependency sort of the dataflow executor) 8=shard_copy (a sharded epoch's copy of the owner's table)
+ * 9=shard_merge (the owner's merge of the per-GPU coverage counts) */
 int faucet_session_kernel_ms(faucet_session* s, int which, float* ms_out, uint64_t* launches_out);
 
 /* ---- multi-GPU: one process per GPU of one NVSwitch box, peer HBM mapped through CUDA IPC -----
@@ -209,6 +212,8 @@ enum { FAUCET_BUF_INVAL = 0, FAUCET_BUF_PACKED, FAUCET_BUF_FLAGS, FAUCET_BUF_SEQ
        FAUCET_BUF_BLOO1_LOCAL, FAUCET_BUF_BLOOM,
        FAUCET_BUF_FLOW_ROWS, FAUCET_BUF_FLOW_PREDS, /* the dependency sort of the shard (faucet_session_flow_prepare);
                                                        exported again per scan -- an all-zero handle = none */
+       FAUCET_BUF_TBL_KEYS, FAUCET_BUF_TBL_RECS, FAUCET_BUF_JSLOT, /* junction table of the stitch (sharded epoch) */
+       FAUCET_BUF_EXACT_LIST, FAUCET_BUF_COV_DELTA,                /* a rank's exact-set list / coverage counts of the epoch */
        FAUCET_BUF_COUNT };
 #define FAUCET_IPC_HANDLE_BYTES 64
 int faucet_session_prepare_multi(faucet_session* s);   /* allocates every exportable buffer */
@@ -221,6 +226,28 @@ int faucet_session_prefix_or(faucet_session* s);
 int faucet_session_or_allreduce(faucet_session* s);
 int faucet_session_import_planes(faucet_session* s, int peer_rank, size_t n_text, uint32_t n_recs, int fastq);
 int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_recs);
+/* ---- the stitch ACROSS GPUs: the sharded epoch (faucet_b200/csrc/shard.cuh; sequenced by faucet_b200/multi.py) ----
+ * The owner (rank 0) runs the first records of its shard through the ordered executor; from there on every rank classifies
+ * ITS OWN records read-only against a replica of the owner's table, the few records that are not quiet (the exact set)
+ * are executed in stream order on every replica, and the owner finally merges the per-rank coverage counts.  Result =
+ * the serial stitch, bit for bit (src/ReadScanner.cpp:61-231, utils/JunctionMap.cpp:533-570).
+ *   every rank:  stitch_begin;  owner: stitch_records(0, r0, 0)
+ *   shard_info -> all-gather -> open_peers(TBL_KEYS, TBL_RECS, JSLOT) -> shard_begin -> open_peers(EXACT_LIST, TBL_KEYS, COV_DELTA)
+ *   repeat { all-gather n_exact; stop when no list grew;  shard_execute; [any need_grow: shard_abort, serial path];  shard_verify }
+ *   shard_finish -> all-gather stats -> owner: shard_merge (others: shard_end) */
+#define FAUCET_SHARD_INFO_BYTES 512
+#define FAUCET_SHARD_STATS 32
+int faucet_session_stitch_records(faucet_session* s, uint32_t begin, uint32_t end, int advance);
+int faucet_session_shard_rows(faucet_session* s, uint32_t r_begin); /* optional: reservation rows ahead of shard_begin */
+int faucet_session_shard_info(faucet_session* s, uint32_t r_begin, int is_owner, void* info_out /* FAUCET_SHARD_INFO_BYTES */);
+int faucet_session_shard_begin(faucet_session* s, const void* infos /* n_ranks x FAUCET_SHARD_INFO_BYTES */, int n_ranks,
+                               int my_rank, int owner, uint32_t* n_exact_out);
+int faucet_session_shard_execute(faucet_session* s, const uint32_t* n_exact /* n_ranks */, int iter, int* need_grow_out);
+int faucet_session_shard_verify(faucet_session* s, uint32_t* n_exact_out);
+int faucet_session_shard_finish(faucet_session* s, uint64_t* stats_out /* FAUCET_SHARD_STATS */);
+int faucet_session_shard_merge(faucet_session* s, const uint64_t* stats_all /* n_ranks x FAUCET_SHARD_STATS */);
+int faucet_session_shard_end(faucet_session* s);
+int faucet_session_shard_abort(faucet_session* s);
 /* host helper: n_shards contiguous, record-aligned, byte-balanced ranges of a FASTA/FASTQ text;
  * offsets_out has n_shards + 1 entries */
 int faucet_host_plan_shards(const char* text, size_t n, int fastq, int n_shards, uint64_t* offsets_out);

@@ -24,13 +24,16 @@ def main():
     text = open(path, "rb").read()
     res = {"rank": rank, "ok": True, "msg": ""}
     try:
-        for (k, j, no_cleaning) in ((31, 1, 1), (21, 0, 0)):
+        # (k, j, no_cleaning, share of shard 0 that rank 0 runs in order before the sharded epoch, forced fallback)
+        for (k, j, no_cleaning, prefix_pct, force_abort) in ((31, 1, 1, 100, 0), (31, 1, 1, 30, 0), (27, 2, 1, 0, 0), (31, 1, 1, 50, 1),
+                                                            (21, 0, 0, 100, 0)):
             _, lt, nh = fb.geometry_from_reads(60000, 30000, 0.04)
             shards = fb.plan_shards(text, True, world)
             a, b = shards[rank]
             cap = max(y - x for x, y in shards) + 1024
             s = fb.Session(k, lt, nh, j=j, max_spacer_dist=100, max_text_bytes=cap)
-            job = ShardedJob(s, TorchComm(torch.device("cuda", local)))
+            fb.set_tuning("shard_force_abort", force_abort)
+            job = ShardedJob(s, TorchComm(torch.device("cuda", local)), prefix_pct=prefix_pct)
             job.setup()
             o = Oracle()
             o1, o2, _ = o.load_two_filters(text, True, k, lt, nh)
@@ -46,6 +49,9 @@ def main():
                 gspf[:] = 0
                 glpf[:] = 0
                 job.scan(True, True, no_cleaning, gspf, sg, glpf, lg)
+                want = "serial (not eligible)" if not no_cleaning else "serial (table growth)" if force_abort else "sharded"
+                assert job.last_scan["mode"] == want, (job.last_scan, want)
+                res.setdefault("scans", []).append(job.last_scan)
                 if rank == 0:
                     grecs, gst = s.junctions()
                     assert gst == ost, (gst, ost)
