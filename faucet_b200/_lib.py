@@ -87,6 +87,7 @@ def _load():
     L.faucet_session_parse.argtypes = [vp, C.c_int]
     L.faucet_session_load.argtypes = [vp]
     L.faucet_session_scan_flags.argtypes = [vp]
+    L.faucet_session_scan_flags_records.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.faucet_session_stitch.argtypes = [vp, C.c_int, C.c_int, _u64p]
     L.faucet_session_stitch_begin.argtypes = [vp, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
     L.faucet_session_stitch_batch.argtypes = [vp]
@@ -302,8 +303,11 @@ class Session:
     def load(self):
         _check(lib.faucet_session_load(self.h))
 
-    def scan_flags(self):
-        _check(lib.faucet_session_scan_flags(self.h))
+    def scan_flags(self, r_begin=None, r_end=None):
+        if r_begin is None:
+            _check(lib.faucet_session_scan_flags(self.h))
+        else:
+            _check(lib.faucet_session_scan_flags_records(self.h, r_begin, r_end))
 
     def stitch(self, paired_ends, no_cleaning):
         n = C.c_uint64()
@@ -342,7 +346,7 @@ class Session:
 
     # ---- multi-GPU stage API (include/faucet_gpu.h, "multi-GPU") ----
     BUFFERS = {"inval": 0, "packed": 1, "flags": 2, "seq_start": 3, "seq_end": 4, "bloo1_local": 5, "bloom": 6, "flow_rows": 7, "flow_preds": 8,
-               "tbl_keys": 9, "tbl_recs": 10, "jslot": 11, "exact_list": 12, "cov_delta": 13}
+               "tbl_keys": 9, "tbl_recs": 10, "jslot": 11, "tbl_pack": 12, "exact_list": 13, "cov_delta": 14}
 
     def prepare_multi(self):
         _check(lib.faucet_session_prepare_multi(self.h))

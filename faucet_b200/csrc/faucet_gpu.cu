@@ -193,6 +193,11 @@ struct faucet_session {
            *mb_span_sums = nullptr;
   uint8_t* mb_flags = nullptr;
   size_t mb_entries_cap = 0, mb_pos_cap = 0;
+  PackedJunction* d_tbl_pack = nullptr;     // owner: T0 as the other GPUs fetch it (16 bytes per junction)
+  unsigned long long tbl_pack_cap = 0;      // entries
+  unsigned int* d_pack_n = nullptr;
+  PackedJunction* d_tbl_in = nullptr;       // others: the local copy of the owner's pack
+  unsigned long long tbl_in_cap = 0;
   const uint32_t* cur_gid = nullptr;        // global record indices of the batch the executor runs (NULL: rec_base + index)
   struct Shard {
     bool active = false, snapshot = false, ran = false;
@@ -462,7 +467,7 @@ void faucet_session_destroy(faucet_session* s) {
   cudaFree(s->d_frows); cudaFree(s->d_fpreds); cudaFree(s->d_fdone); cudaFree(s->d_fcounts); cudaFree(s->d_fcount_sums);
   cudaFree(s->d_fpairs); cudaFree(s->d_fpairs2); cudaFree(s->d_fhist); cudaFree(s->d_fhist_sums); cudaFree(s->d_fbig); cudaFree(s->d_in_exact);
   cudaFree(s->d_list); cudaFree(s->d_eprefix); cudaFree(s->d_eprefix_sums); cudaFree(s->d_count); cudaFree(s->d_snap_keys); cudaFree(s->d_snap_recs);
-  cudaFree(s->d_st_snap); cudaFree(s->d_spf_snap); cudaFree(s->d_cov_delta); cudaFree(s->d_st_quiet);
+  cudaFree(s->d_st_snap); cudaFree(s->d_spf_snap); cudaFree(s->d_cov_delta); cudaFree(s->d_st_quiet); cudaFree(s->d_tbl_pack); cudaFree(s->d_pack_n); cudaFree(s->d_tbl_in);
   cudaFree(s->mb_inval); cudaFree(s->mb_packed); cudaFree(s->mb_seq_start); cudaFree(s->mb_seq_end); cudaFree(s->mb_gid); cudaFree(s->mb_span); cudaFree(s->mb_span_sums); cudaFree(s->mb_flags);
   cudaFree(s->d_deferred[0]); cudaFree(s->d_deferred[1]); cudaFree(s->d_spf); cudaFree(s->d_ext);
   faucet_session_close_peers(s);
@@ -730,12 +735,23 @@ static int memo_acquire(faucet_session* s, int kind, int* qbits) {
   return 0;
 }
 
-int faucet_session_scan_flags(faucet_session* s) {
+int faucet_session_scan_flags(faucet_session* s) { return faucet_session_scan_flags_records(s, 0, s->n_recs); }
+
+// the flag bytes of the records [r_begin, r_end) only (a sharded epoch's owner flags the records of its ordered prefix
+// first, the others once the table is on its way to the other GPUs); (0, n_recs) = the whole batch
+int faucet_session_scan_flags_records(faucet_session* s, uint32_t r_begin, uint32_t r_end) {
   if (!s->parsed) return fail(FAUCET_E_STATE, "faucet_session_scan_flags before faucet_session_parse");
+  if (r_begin > r_end || r_end > s->n_recs) return fail(FAUCET_E_ARG, "bad record range");
   int rc = ensure_scan_buffers(s);
   if (rc) return rc;
+  // byte range of those records: from the sequence line of the first one to the end of the sequence line of the last
+  uint32_t b0 = 0, b1 = (uint32_t)s->n;
+  if (r_begin == r_end) return 0;
+  if (r_begin > 0) CU(cudaMemcpyAsync(&b0, s->d_seq_start + r_begin, 4, cudaMemcpyDeviceToHost, s->stream));
+  if (r_end < s->n_recs) CU(cudaMemcpyAsync(&b1, s->d_seq_end + r_end - 1, 4, cudaMemcpyDeviceToHost, s->stream));
+  if (r_begin > 0 || r_end < s->n_recs) CU(cudaStreamSynchronize(s->stream));
   ScanArgs a;
-  a.inval = s->d_inval; a.packed = s->d_packed; a.n_words = (uint32_t)((s->n + 31) / 32);
+  a.inval = s->d_inval; a.packed = s->d_packed; a.w_begin = b0 / 32; a.n_words = (uint32_t)(((size_t)b1 + 31) / 32);
   a.bloom = s->d_bloom; a.wmask = (uint32_t)((s->tai() - 1) >> 5); a.k = s->k; a.j = s->j; a.n_hash = s->n_hash; a.flags = s->d_flags;
   const int grid = g.sm_count * SCAN_CTAS_PER_SM * 2;  // two full waves of resident CTAs
   a.memo = nullptr; a.memo_mask = 0; a.dbg = nullptr;
@@ -1458,6 +1474,7 @@ static void* session_buffer(faucet_session* s, int what) {
     case FAUCET_BUF_FLOW_PREDS: return s->prep_valid && !s->prep_big ? s->d_fpreds : nullptr;
     case FAUCET_BUF_TBL_KEYS: return s->d_keys;
     case FAUCET_BUF_TBL_RECS: return s->d_recs;
+    case FAUCET_BUF_TBL_PACK: return s->d_tbl_pack;
     case FAUCET_BUF_JSLOT: return s->d_jslot;
     case FAUCET_BUF_EXACT_LIST: return s->d_list;
     case FAUCET_BUF_COV_DELTA: return s->d_cov_delta;
@@ -1477,8 +1494,8 @@ int faucet_session_prepare_multi(faucet_session* s) {
 int faucet_session_export(faucet_session* s, int what, void* handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) == FAUCET_IPC_HANDLE_BYTES, "handle size");
   void* p = session_buffer(s, what);
-  if (!p && (what == FAUCET_BUF_FLOW_ROWS || what == FAUCET_BUF_FLOW_PREDS)) {  // no prepared sort: an all-zero handle says so
-    memset(handle_out, 0, FAUCET_IPC_HANDLE_BYTES);
+  if (!p && what >= FAUCET_BUF_FLOW_ROWS && what < FAUCET_BUF_COUNT) {  // optional buffers (no prepared sort, not the owner
+    memset(handle_out, 0, FAUCET_IPC_HANDLE_BYTES);                     // of the table, ...): an all-zero handle says so
     return 0;
   }
   if (!p) return fail(FAUCET_E_STATE, "buffer not allocated yet (call faucet_session_prepare_multi first)");
@@ -1690,6 +1707,27 @@ int faucet_session_shard_info(faucet_session* s, uint32_t r_begin, int is_owner,
     while (s->h_st.n_entries + s->h_st.n_entries / 8 + bound + 65536 > s->tbl_cap / 2)
       if ((rc = stitch_grow_table(s))) return rc;
   }
+  if (is_owner) {  // T0 as the other GPUs will fetch it
+    if (s->tbl_pack_cap != s->tbl_cap / 2 + 2) {
+      cudaFree(s->d_tbl_pack); s->d_tbl_pack = nullptr;
+      s->tbl_pack_cap = s->tbl_cap / 2 + 2;
+      if ((rc = dmalloc(&s->d_tbl_pack, s->tbl_pack_cap))) return rc;
+    }
+    if (!s->d_pack_n && (rc = dmalloc(&s->d_pack_n, 1))) return rc;
+    StitchArgs a;
+    stitch_fill_args(s, a);
+    unsigned int n_packed = 0;
+    {
+      KTimer kt(s, KT_SHARD_COPY);
+      CU(cudaMemsetAsync(s->d_pack_n, 0, 4, s->stream));
+      shard_pack_kernel<<<g.sm_count * 8, 256, 0, s->stream>>>(a, s->d_tbl_pack, s->d_pack_n);
+      s->launches++;
+    }
+    CU(cudaMemcpyAsync(&n_packed, s->d_pack_n, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if ((rc = check_launch("shard_pack"))) return rc;
+    if (n_packed != s->h_st.n_entries) return fail(FAUCET_E_CUDA, "sharded epoch: packed junction count differs from the table's entry counter");
+  }
   in.n_text = s->n; in.rec_base = s->rec_base; in.tbl_cap = s->tbl_cap; in.n_recs = s->n_recs; in.r_begin = r_begin;
   in.fastq = s->fastq; in.eligible = (s->d_spf || s->lpf.enabled() || g.stitch_exec == 0) ? 0u : 1u;
   in.st = s->h_st;
@@ -1750,13 +1788,27 @@ int faucet_session_shard_begin(faucet_session* s, const void* infos, int n_ranks
       s->d_keys = nullptr; s->d_recs = nullptr; s->d_jstamps = nullptr; s->tbl_cap = 0;
       if ((rc = stitch_alloc_table(s, cap))) return rc;
     }
-    const void *pk = s->peer[FAUCET_BUF_TBL_KEYS][owner], *pr = s->peer[FAUCET_BUF_TBL_RECS][owner], *pj = s->peer[FAUCET_BUF_JSLOT][owner];
-    if (!pk || !pr || !pj) return fail(FAUCET_E_STATE, "the owner's table is not opened");
+    const void *pp = s->peer[FAUCET_BUF_TBL_PACK][owner], *pj = s->peer[FAUCET_BUF_JSLOT][owner];
+    if (!pp || !pj) return fail(FAUCET_E_STATE, "the owner's table is not opened");
+    const unsigned long long n_in = in[owner].st.n_entries;
+    if (n_in > s->tbl_in_cap) {
+      cudaFree(s->d_tbl_in); s->d_tbl_in = nullptr;
+      s->tbl_in_cap = n_in + n_in / 4 + 4096;
+      if ((rc = dmalloc(&s->d_tbl_in, s->tbl_in_cap))) return rc;
+    }
     {
       KTimer kt(s, KT_SHARD_COPY);
-      CU(cudaMemcpyAsync(s->d_keys, pk, (cap + 1) * 8, cudaMemcpyDeviceToDevice, s->stream));
-      CU(cudaMemcpyAsync(s->d_recs, pr, (cap + 1) * REC_WORDS * 4, cudaMemcpyDeviceToDevice, s->stream));
+      CU(cudaMemsetAsync(s->d_keys, 0xff, (cap + 1) * 8, s->stream));
+      CU(cudaMemsetAsync(s->d_recs, 0, (cap + 1) * REC_WORDS * 4, s->stream));
+      if (n_in) CU(cudaMemcpyAsync(s->d_tbl_in, pp, n_in * sizeof(PackedJunction), cudaMemcpyDeviceToDevice, s->stream));
       CU(cudaMemcpyAsync(s->d_jslot, pj, (((size_t)1 << g.res_log2) / 32 + 1) * 4, cudaMemcpyDeviceToDevice, s->stream));
+      if (n_in) {
+        StitchArgs a;
+        stitch_fill_args(s, a);
+        a.cap = cap;
+        shard_unpack_kernel<<<(unsigned)std::min<unsigned long long>((n_in + 255) / 256, (unsigned long long)g.sm_count * 16), 256, 0, s->stream>>>(a, s->d_tbl_in, (unsigned int)n_in);
+        s->launches++;
+      }
     }
     s->h_st = in[owner].st;
     std::memset(s->h_st.stats, 0, sizeof s->h_st.stats);  // the counters of T0 live on the owner

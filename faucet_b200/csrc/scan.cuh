@@ -41,7 +41,8 @@ constexpr int MAX_J = 4;     // JChecker scratch arrays hold 1000 k-mers => j <=
 struct ScanArgs {
   const uint32_t* inval;
   const uint32_t* packed;
-  uint32_t n_words;
+  uint32_t n_words;       // the words [w_begin, n_words) of the text (32 byte offsets each) are scanned
+  uint32_t w_begin;
   const uint32_t* bloom;  // bloo2, plain reference layout viewed as little-endian u32 words
   uint32_t wmask;         // (tai - 1) >> 5: word index mask (log2_tai <= 37, checked by the session)
   int k, j, n_hash;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_ker
   ScanQueue& q = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t warp = (blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5;
+  const uint32_t warp = a.w_begin + ((blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5);
   const uint32_t n_warps = (gridDim.x * SCAN_THREADS) >> 5;
   const int nh = NH ? NH : a.n_hash;
   const int k = a.k;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, SCAN_CTAS_PER_SM) scan_flags_mem
   ScanQueueM& q = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t warp = (blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5;
+  const uint32_t warp = a.w_begin + ((blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5);
   const uint32_t n_warps = (gridDim.x * SCAN_THREADS) >> 5;
   const int nh = NH ? NH : a.n_hash;
   const int k = a.k;

@@ -8,13 +8,14 @@
 // GPU that owns the records, all GPUs at once:
 //
 //   prefix     GPU 0 runs the first records of shard 0 through the ordered executor: the table T0.
-//   replicate  every other GPU copies T0's keys / distances / links out of GPU 0's HBM (NVLink).
+//   replicate  every other GPU copies T0's keys / distances / links -- packed by GPU 0 into 16 bytes per junction -- out of
+//              GPU 0's HBM (NVLink) and rebuilds the table locally.
 //   classify   every GPU walks ITS OWN records read-only against its replica of T0, all records in parallel.  A quiet
 //              record commits at once: coverage counts into the GPU's own count array (4 u32 per table slot), scan
 //              counters into the GPU's own counter block.  The others form the exact set E (per-shard ascending lists).
 //   execute    EVERY GPU runs the WHOLE exact set -- the lists of all shards, in stream order -- through the ordered
-//              executor on its own replica, reading the few lines of foreign shards straight from their owner's planes
-//              over NVLink.  The executor is sequential-equivalent, hence deterministic in everything a walk reads
+//              executor on its own replica; the lines of foreign shards are gathered from their owner's planes over
+//              NVLink into one small local batch first.  The executor is sequential-equivalent, hence deterministic in everything a walk reads
 //              (keys, distances, links, creation stamps): all replicas stay identical in those fields without a single
 //              message, and so do the per-slot "written by" marks (global record indices).
 //   verify     every GPU checks its own quiet records against the marks: a record with an earlier write under one of its
@@ -91,6 +92,56 @@ __global__ void __launch_bounds__(256) shard_gather_copy_kernel(GatherArgs g, ui
     const uint32_t nls = off + (ls & 31u);
     for (uint32_t t = lane; t < len; t += 32) g.o_flags[nls + t] = g.flags[r][ls + t];
     if (lane == 0) { g.o_seq_start[i] = nls; g.o_seq_end[i] = nls + len; g.o_gid[i] = g.rec_base[r] + rec; }
+  }
+}
+
+// ---- T0 for the other GPUs: what a walk reads of a junction, 16 bytes per OCCUPIED slot instead of 72 per slot
+struct PackedJunction {
+  unsigned long long key;
+  uint8_t dist[5];
+  uint8_t link;
+  uint8_t pad[2];
+};
+static_assert(sizeof(PackedJunction) == 16, "PackedJunction layout");
+
+__global__ void shard_pack_kernel(StitchArgs a, PackedJunction* __restrict__ out, unsigned int* __restrict__ n_out) {
+  const int lane = threadIdx.x & 31;
+  for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base <= a.cap;
+       base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = base + lane;
+    bool occ = false;
+    if (i < a.cap) occ = a.keys[i] != KEY_EMPTY;
+    else if (i == a.cap) occ = *a.special != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, occ);
+    if (!m) continue;
+    unsigned int at = 0;
+    if (lane == 0) at = atomicAdd(n_out, (unsigned int)__popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+    if (occ) {
+      const uint32_t* r = a.recs + i * REC_WORDS;
+      PackedJunction p;
+      p.key = i == a.cap ? KEY_EMPTY : a.keys[i];
+      for (int f = 0; f < 5; f++) p.dist[f] = (uint8_t)r[REC_DIST + f];
+      p.link = (uint8_t)r[REC_LINK];
+      p.pad[0] = p.pad[1] = 0;
+      out[at] = p;
+    }
+  }
+}
+// into a cleared table (keys all KEY_EMPTY, records zero); the entry counter and the KEY_EMPTY flag come with the state block
+__global__ void shard_unpack_kernel(StitchArgs a, const PackedJunction* __restrict__ in, unsigned int n) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const PackedJunction p = in[i];
+    unsigned long long h;
+    if (p.key == KEY_EMPTY) {
+      h = a.cap;
+    } else {
+      h = mix64(p.key) & (a.cap - 1);
+      while (atomicCAS(a.keys + h, KEY_EMPTY, p.key) != KEY_EMPTY) h = (h + 1) & (a.cap - 1);
+    }
+    uint32_t* r = a.recs + h * REC_WORDS;
+    for (int f = 0; f < 5; f++) r[REC_DIST + f] = p.dist[f];
+    r[REC_LINK] = p.link;
   }
 }
 

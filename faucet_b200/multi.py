@@ -63,7 +63,7 @@ PLANES = ("inval", "packed", "flags", "seq_start", "seq_end")
 
 
 class ShardedJob:
-    def __init__(self, engine, comm, sharded_stitch=True, prefix_pct=100):
+    def __init__(self, engine, comm, sharded_stitch=True, prefix_pct=60):
         """sharded_stitch: take the sharded epoch when the scan allows it; prefix_pct: share of shard 0 that rank 0
         runs through the ordered executor before the epoch starts (the dense start of the stream)"""
         self.eng, self.comm = engine, comm
@@ -114,9 +114,12 @@ class ShardedJob:
     def scan(self, fastq, paired_ends, no_cleaning, spf=None, spf_geom=(0, 0), lpf=None, lpf_geom=(0, 0)):
         """pass 2; rank 0 ends up holding the junction map (engine.junctions())"""
         e = self.eng
-        e.scan_flags()
-        if self.sharded_stitch and self.world > 1 and hasattr(e, "shard_info"):
+        # (every rank is called with the same arguments: the scan can be sharded unless it feeds pair filters)
+        if (self.sharded_stitch and self.world > 1 and hasattr(e, "shard_info")
+                and (no_cleaning or (spf is None and lpf is None))):
             return self._scan_sharded(fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom)
+        e.scan_flags()
+        self.last_scan = {"mode": "serial"}
         return self._scan_serial(fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom, begun=False)
 
     def _scan_sharded(self, fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom):
@@ -133,12 +136,13 @@ class ShardedJob:
             t = time.perf_counter()
             stat["ms"][name] = round(stat["ms"].get(name, 0.0) + (t - t_last[0]) * 1e3, 3)
             t_last[0] = t
-        # (every rank is called with the same arguments: the scan can be sharded unless it feeds pair filters)
-        if not (no_cleaning or (spf is None and lpf is None)):
-            stat["mode"] = "serial (not eligible)"
-            return self._scan_serial(fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom, begun="batch")
-        if rank > 0 and hasattr(e, "shard_rows"):
-            e.shard_rows(0)  # pure work, done while rank 0 runs its prefix
+        # rank 0 flags the records of its prefix first and the rest once the table is on its way to the others
+        if rank == 0:
+            e.scan_flags(0, r0)
+        else:
+            e.scan_flags()
+            if hasattr(e, "shard_rows"):
+                e.shard_rows(0)  # pure work, done while rank 0 runs its prefix
         if rank == 0 and r0:
             e.stitch_records(0, r0, False)
             e.sync()
@@ -148,9 +152,13 @@ class ShardedJob:
         lap("info")
         if not all(struct.unpack_from("<QQQIIII", b)[6] for b in infos):  # (e.g. the round-based executor was selected)
             stat["mode"] = "serial (not eligible)"
+            if rank == 0:
+                e.scan_flags(r0, n_recs)
             return self._scan_serial(fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom, begun="records", r_begin=r0)
-        self._open(("tbl_keys", "tbl_recs", "jslot"))
+        self._open(("tbl_pack", "jslot"))
         lap("open")
+        if rank == 0:
+            e.scan_flags(r0, n_recs)
         n = e.shard_begin(infos, world, rank, 0)
         lap("classify")
         self._open(("exact_list", "tbl_keys", "cov_delta"))

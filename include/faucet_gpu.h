@@ -169,6 +169,7 @@ int faucet_session_reset_filters(faucet_session* s);           /* zero bloo1/blo
 int faucet_session_parse(faucet_session* s, int fastq);        /* text -> 2-bit + validity planes */
 int faucet_session_load(faucet_session* s);                    /* pass 1 over the parsed batch */
 int faucet_session_scan_flags(faucet_session* s);              /* pass 2, order-free part */
+int faucet_session_scan_flags_records(faucet_session* s, uint32_t r_begin, uint32_t r_end); /* ... of these records only */
 int faucet_session_stitch(faucet_session* s, int paired_ends, int no_cleaning,
                           uint64_t* n_junctions_out);          /* pass 2, stream-order part */
 /* multi-batch form of the stitch: begin once (pair filters may be NULL), then one call per parsed and
@@ -213,6 +214,7 @@ enum { FAUCET_BUF_INVAL = 0, FAUCET_BUF_PACKED, FAUCET_BUF_FLAGS, FAUCET_BUF_SEQ
        FAUCET_BUF_FLOW_ROWS, FAUCET_BUF_FLOW_PREDS, /* the dependency sort of the shard (faucet_session_flow_prepare);
                                                        exported again per scan -- an all-zero handle = none */
        FAUCET_BUF_TBL_KEYS, FAUCET_BUF_TBL_RECS, FAUCET_BUF_JSLOT, /* junction table of the stitch (sharded epoch) */
+       FAUCET_BUF_TBL_PACK,                                       /* the owner's table packed for the other GPUs */
        FAUCET_BUF_EXACT_LIST, FAUCET_BUF_COV_DELTA,                /* a rank's exact-set list / coverage counts of the epoch */
        FAUCET_BUF_COUNT };
 #define FAUCET_IPC_HANDLE_BYTES 64
@@ -232,7 +234,7 @@ int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_rec
  * are executed in stream order on every replica, and the owner finally merges the per-rank coverage counts.  Result =
  * the serial stitch, bit for bit (src/ReadScanner.cpp:61-231, utils/JunctionMap.cpp:533-570).
  *   every rank:  stitch_begin;  owner: stitch_records(0, r0, 0)
- *   shard_info -> all-gather -> open_peers(TBL_KEYS, TBL_RECS, JSLOT) -> shard_begin -> open_peers(EXACT_LIST, TBL_KEYS, COV_DELTA)
+ *   shard_info -> all-gather -> open_peers(TBL_PACK, JSLOT) -> shard_begin -> open_peers(EXACT_LIST, TBL_KEYS, COV_DELTA)
  *   repeat { all-gather n_exact; stop when no list grew;  shard_execute; [any need_grow: shard_abort, serial path];  shard_verify }
  *   shard_finish -> all-gather stats -> owner: shard_merge (others: shard_end) */
 #define FAUCET_SHARD_INFO_BYTES 512

@@ -49,7 +49,7 @@ def main():
                 gspf[:] = 0
                 glpf[:] = 0
                 job.scan(True, True, no_cleaning, gspf, sg, glpf, lg)
-                want = "serial (not eligible)" if not no_cleaning else "serial (table growth)" if force_abort else "sharded"
+                want = "serial" if not no_cleaning else "serial (table growth)" if force_abort else "sharded"
                 assert job.last_scan["mode"] == want, (job.last_scan, want)
                 res.setdefault("scans", []).append(job.last_scan)
                 if rank == 0:
@@ -65,6 +65,10 @@ def main():
         import traceback
         res.update(ok=False, msg=traceback.format_exc())
     json.dump(res, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
+    if not res["ok"]:  # the other ranks may be waiting in a collective: let torchrun tear the job down
+        sys.stderr.write(res["msg"])
+        sys.stderr.flush()
+        os._exit(1)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -27,8 +27,10 @@ def test_sharded_job_on_gpus(tmp_path, world):
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), path, str(tmp_path)]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     res = [json.load(open(f)) for f in sorted(glob.glob(str(tmp_path / "rank*.json")))]
+    for r in res:
+        assert r["ok"], r["msg"]
     assert p.returncode == 0, p.stderr[-3000:]
     assert len(res) == world
     for r in res:

@@ -2,7 +2,7 @@
 N=$1; PCTS=$2; shift 2
 export FAUCET_BENCH_SKIP_EXTRAS=1
 for pct in $PCTS; do
-  FAUCET_SHARD_PREFIX_PCT=$pct timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+pct)) bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/r2s_bench_n${N}_p$pct.json 2> gpurun_out/r2s_bench_n${N}_p${pct}_err.log; echo "bench n=$N pct=$pct rc=$?"
+  FAUCET_SHARD_PREFIX_PCT=$pct timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+pct)) bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/r2s_bench_n${N}_p$pct.json 2> gpurun_out/r2s_bench_n${N}_p${pct}_err.log; echo "bench n=$N pct=$pct rc=$?"
   python - <<PY
 import json
 try:
