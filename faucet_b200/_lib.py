@@ -92,6 +92,7 @@ def _load():
     L.faucet_session_stitch_begin.argtypes = [vp, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
     L.faucet_session_stitch_batch.argtypes = [vp]
     L.faucet_session_flow_prepare.argtypes = [vp]
+    L.faucet_session_flow_prepare_records.argtypes = [vp, C.c_uint32, C.c_int]
     L.faucet_session_get_bloom.argtypes = [vp, _u8p, _u8p]
     L.faucet_session_set_bloom.argtypes = [vp, _u8p]
     L.faucet_session_read_bloom.argtypes = [vp, _u8p]
@@ -385,8 +386,11 @@ class Session:
         _check(lib.faucet_session_stitch_begin(self.h, int(paired_ends), int(no_cleaning), _ptr(spf), spf_geom[0],
                                                spf_geom[1], _ptr(lpf), lpf_geom[0], lpf_geom[1]))
 
-    def flow_prepare(self):
-        _check(lib.faucet_session_flow_prepare(self.h))
+    def flow_prepare(self, n=None, concurrent=False):
+        if n is None:
+            _check(lib.faucet_session_flow_prepare(self.h))
+        else:
+            _check(lib.faucet_session_flow_prepare_records(self.h, n, int(concurrent)))
 
     def stitch_batch(self):
         _check(lib.faucet_session_stitch_batch(self.h))

@@ -87,6 +87,7 @@ struct faucet_session {
   // of the current one (whole-pass entry points); the second one is allocated on first use
   uint8_t* d_textbufs[3] = {nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // a sort running next to the session's stream (flow_prepare_records)
   cudaEvent_t ev_copied[3] = {nullptr, nullptr, nullptr};
   uint8_t* d_text = nullptr;  // the current batch
   size_t n = 0;               // bytes in the current batch
@@ -201,7 +202,7 @@ struct faucet_session {
   const uint32_t* cur_gid = nullptr;        // global record indices of the batch the executor runs (NULL: rec_base + index)
   struct Shard {
     bool active = false, snapshot = false, ran = false;
-    int owner = 0;
+    int owner = 0, iter = 0;
     uint32_t r_begin = 0;                   // this GPU's records [r_begin, n_recs) belong to the epoch
     uint64_t rec_base[MAX_PEERS + 1] = {};  // global index of record 0 of every shard; [n_ranks] = records of the stream
     uint32_t n_recs[MAX_PEERS] = {};
@@ -455,6 +456,7 @@ void faucet_session_destroy(faucet_session* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   drain_events(s);
   if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+  if (s->aux_stream) { cudaStreamSynchronize(s->aux_stream); cudaStreamDestroy(s->aux_stream); }
   for (int i = 0; i < 3; i++) { cudaFree(s->d_textbufs[i]); if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]); }
   cudaFree(s->d_inval); cudaFree(s->d_packed); cudaFree(s->d_skipA);
   cudaFree(s->d_pend); cudaFree(s->d_chunk); cudaFree(s->d_pctr); cudaFree(s->d_lctr);
@@ -1080,14 +1082,28 @@ static int flow_prepare(faucet_session* s, const uint32_t* list, uint32_t b0, ui
 }
 
 // prepares the whole parsed batch ahead of its stitch (stage API; pass 1 with retained planes; shard owners)
-int faucet_session_flow_prepare(faucet_session* s) {
+int faucet_session_flow_prepare(faucet_session* s) { return faucet_session_flow_prepare_records(s, s->n_recs, 0); }
+
+// ... or its first n records (a sorted prefix serves every shorter prefix: predecessors are earlier records).
+// concurrent != 0: the sort runs on a second stream, next to what is queued on the session's (a sharded epoch's owner
+// sorts the records of its ordered prefix while scan_flags flags them: one is memory-bound, the other instruction-bound);
+// the call returns when the sort is complete.
+int faucet_session_flow_prepare_records(faucet_session* s, uint32_t n, int concurrent) {
   if (!s->parsed) return fail(FAUCET_E_STATE, "flow_prepare before parse");
+  if (n > s->n_recs) return fail(FAUCET_E_ARG, "bad record count");
   s->prep_valid = false;
-  if (g.stitch_exec == 0 || s->n_recs == 0 || s->n_recs > g.flow_chunk) return 0;  // nothing to keep: the stitch sorts itself
+  if (g.stitch_exec == 0 || n == 0 || n > g.flow_chunk) return 0;  // nothing to keep: the stitch sorts itself
   bool big = false;
-  int rc = flow_prepare(s, nullptr, 0, s->n_recs, &big);
+  cudaStream_t main_stream = s->stream;
+  if (concurrent) {
+    if (!s->aux_stream) CU(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+    s->stream = s->aux_stream;
+  }
+  int rc = flow_prepare(s, nullptr, 0, n, &big);
+  if (!rc && concurrent && cudaStreamSynchronize(s->aux_stream) != cudaSuccess) rc = fail(FAUCET_E_CUDA, "flow_prepare (second stream)");
+  s->stream = main_stream;
   if (rc) return rc;
-  s->prep_valid = true; s->prep_n = s->n_recs; s->prep_big = big;
+  s->prep_valid = true; s->prep_n = n; s->prep_big = big;
   s->prep_rows = s->d_frows; s->prep_preds = s->d_fpreds;
   return 0;
 }
@@ -1105,7 +1121,7 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
   for (uint32_t b0 = begin; b0 < end;) {
     const uint32_t n = std::min<uint32_t>(end - b0, g.flow_chunk);
     // (a dependency sort of the whole batch also serves any prefix of it: predecessors are earlier records)
-    const bool prepared = !list && b0 == 0 && s->prep_valid && s->prep_n == s->n_recs && n <= s->prep_n && end <= g.flow_chunk;
+    const bool prepared = !list && b0 == 0 && s->prep_valid && n <= s->prep_n && end <= g.flow_chunk;
     bool big = false;
     const uint32_t *rows = s->prep_rows, *preds = s->prep_preds;
     if (prepared) {
@@ -1183,7 +1199,7 @@ static int stitch_ensure_epoch_buffers(faucet_session* s, uint32_t m) {
     cudaFree(s->d_list); cudaFree(s->d_eprefix); cudaFree(s->d_eprefix_sums);
     s->d_list = nullptr; s->d_eprefix = nullptr; s->d_eprefix_sums = nullptr;
     s->list_cap = (size_t)m + m / 4 + 1024;
-    if ((rc = dmalloc(&s->d_list, s->list_cap)) || (rc = dmalloc(&s->d_eprefix, s->list_cap)) ||
+    if ((rc = dmalloc(&s->d_list, 2 * s->list_cap)) || (rc = dmalloc(&s->d_eprefix, s->list_cap)) ||  // (two lists: sharded epochs alternate)
         (rc = dmalloc(&s->d_eprefix_sums, s->list_cap / SCAN_CHUNK + 2)))
       return rc;
   }
@@ -1470,8 +1486,8 @@ static void* session_buffer(faucet_session* s, int what) {
     case FAUCET_BUF_SEQ_END: return s->d_seq_end;
     case FAUCET_BUF_BLOO1_LOCAL: return s->d_b1local;
     case FAUCET_BUF_BLOOM: return s->d_bloom;
-    case FAUCET_BUF_FLOW_ROWS: return s->prep_valid && !s->prep_big ? s->d_frows : nullptr;
-    case FAUCET_BUF_FLOW_PREDS: return s->prep_valid && !s->prep_big ? s->d_fpreds : nullptr;
+    case FAUCET_BUF_FLOW_ROWS: return s->prep_valid && !s->prep_big && s->prep_n == s->n_recs ? s->d_frows : nullptr;
+    case FAUCET_BUF_FLOW_PREDS: return s->prep_valid && !s->prep_big && s->prep_n == s->n_recs ? s->d_fpreds : nullptr;
     case FAUCET_BUF_TBL_KEYS: return s->d_keys;
     case FAUCET_BUF_TBL_RECS: return s->d_recs;
     case FAUCET_BUF_TBL_PACK: return s->d_tbl_pack;
@@ -1664,8 +1680,9 @@ void shard_dry(faucet_session* s, const StitchArgs& d, int mode, uint8_t want, u
   stitch_dry_kernel<<<g.sm_count * 8, DRY_THREADS, DRY_WARPS * sizeof(DryScratch), s->stream>>>(w);
   s->launches++;
 }
-// the ascending list of this GPU's members of the exact set -> d_list; their number
-int shard_list(faucet_session* s, uint32_t* n_out) {
+// the ascending list of this GPU's members of the exact set -> list buffer `sel` (d_list + sel x n_recs: the ranks
+// alternate between two buffers, so a rank may write its next list while a peer still reads the current one); their number
+int shard_list(faucet_session* s, int sel, uint32_t* n_out) {
   const uint32_t r = s->shard.r_begin, m = s->n_recs - r;
   *n_out = 0;
   if (!m) return 0;
@@ -1677,7 +1694,7 @@ int shard_list(faucet_session* s, uint32_t* n_out) {
     scan_reduce_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
     scan_sums_kernel<<<1, 1024, 0, s->stream>>>(s->d_eprefix_sums, n_blocks);
     scan_apply_kernel<<<n_blocks, 256, 0, s->stream>>>(s->d_eprefix, m, s->d_eprefix_sums);
-    exact_list_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix, s->d_list, s->d_count);
+    exact_list_kernel<<<grid, 256, 0, s->stream>>>(s->d_in_exact, r, m, s->d_eprefix, s->d_list + (size_t)sel * s->n_recs, s->d_count);
     s->launches += 5;
   }
   CU(cudaMemcpyAsync(n_out, s->d_count, 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1819,7 +1836,7 @@ int faucet_session_shard_begin(faucet_session* s, const void* infos, int n_ranks
   }
   s->rec_base = sh.rec_base[my_rank];
   const uint32_t m = s->n_recs - sh.r_begin;
-  if ((rc = stitch_ensure_epoch_buffers(s, std::max<uint32_t>(m, 1)))) return rc;
+  if ((rc = stitch_ensure_epoch_buffers(s, std::max<uint32_t>(s->n_recs, 1)))) return rc;  // (lists: two buffers n_recs apart)
   if (s->cov_delta_cap != cap) {
     cudaFree(s->d_cov_delta); s->d_cov_delta = nullptr; s->cov_delta_cap = 0;
     if ((rc = dmalloc(&s->d_cov_delta, (cap + 1) * 4))) return rc;
@@ -1838,7 +1855,8 @@ int faucet_session_shard_begin(faucet_session* s, const void* infos, int n_ranks
   if ((rc = stitch_snapshot(s))) return rc;
   sh.snapshot = true;
   s->ep.classify_epochs++; s->ep.dry_records += m;
-  if ((rc = shard_list(s, n_exact_out))) return rc;
+  sh.iter = 0;
+  if ((rc = shard_list(s, 0, n_exact_out))) return rc;
   s->ep.nonquiet += *n_exact_out;
   return 0;
 }
@@ -1852,6 +1870,8 @@ int faucet_session_shard_execute(faucet_session* s, const uint32_t* n_exact, int
   if (!sh.active) return fail(FAUCET_E_STATE, "no sharded epoch is open");
   *need_grow_out = 0;
   int rc;
+  if (iter != sh.iter) return fail(FAUCET_E_STATE, "shard_execute: iterations out of step");
+  sh.iter = iter + 1;  // (the list shard_verify builds next goes to the other buffer)
   if (iter > 0 && (rc = stitch_restore(s, 0))) return rc;
   CU(cudaMemsetAsync(s->d_dirty, 0xff, ((size_t)1 << g.res_log2) * 4, s->stream));
   CU(cudaMemsetAsync(s->d_dirty_max, 0, ((size_t)1 << g.res_log2) * 4, s->stream));
@@ -1872,6 +1892,7 @@ int faucet_session_shard_execute(faucet_session* s, const uint32_t* n_exact, int
     ga.seq_start[r] = me ? s->d_seq_start : (const uint32_t*)s->peer[FAUCET_BUF_SEQ_START][r];
     ga.seq_end[r] = me ? s->d_seq_end : (const uint32_t*)s->peer[FAUCET_BUF_SEQ_END][r];
     ga.list[r] = me ? s->d_list : (const uint32_t*)s->peer[FAUCET_BUF_EXACT_LIST][r];
+    if (ga.list[r]) ga.list[r] += (size_t)(iter & 1) * sh.n_recs[r];
     if (n_exact[r] && (!ga.list[r] || !ga.packed[r] || !ga.inval[r] || !ga.flags[r] || !ga.seq_start[r] || !ga.seq_end[r]))
       return fail(FAUCET_E_STATE, "a peer's exact list / planes are not opened");
   }
@@ -1950,7 +1971,7 @@ int faucet_session_shard_verify(faucet_session* s, uint32_t* n_exact_out) {
     shard_dry(s, d, DRY_RECHECK, EX_RECHECK, 0, true);
     shard_dry(s, d, DRY_RETRACT, EX_COMMITTED, EX_RETRACTED, false);
   }
-  return shard_list(s, n_exact_out);
+  return shard_list(s, sh.iter & 1, n_exact_out);
 }
 
 // Step 4: the settled records (they saw the replica as the last exact run left it) move their commit from the walk on T0

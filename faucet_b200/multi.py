@@ -44,9 +44,10 @@ class TorchComm:
         t = self.torch.frombuffer(bytearray(blob), dtype=self.torch.uint8)
         if self.device is not None:
             t = t.to(self.device)
-        out = [self.torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t)
-        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+        out = self.torch.empty(self.world * t.numel(), dtype=self.torch.uint8, device=t.device)
+        self.dist.all_gather_into_tensor(out, t)
+        raw = out.cpu().numpy().tobytes()  # one copy back for all ranks' blobs
+        return [raw[i * len(blob):(i + 1) * len(blob)] for i in range(self.world)]
 
 
 class SoloComm:
@@ -100,9 +101,6 @@ class ShardedJob:
         e.sync()
         self.comm.barrier()
 
-    def _gather_u32(self, v):
-        return [struct.unpack("<I", b)[0] for b in self.comm.all_gather_bytes(struct.pack("<I", v))]
-
     def _open(self, names, blank=False):
         """(buffers may have moved since the last scan: exported each time; one exchange for all of them)"""
         e = self.eng
@@ -139,6 +137,8 @@ class ShardedJob:
         # rank 0 flags the records of its prefix first and the rest once the table is on its way to the others
         if rank == 0:
             e.scan_flags(0, r0)
+            if r0:
+                e.flow_prepare(r0, concurrent=True)  # the dependency sort of the prefix, next to the flagging of its records
         else:
             e.scan_flags()
             if hasattr(e, "shard_rows"):
@@ -163,23 +163,22 @@ class ShardedJob:
         lap("classify")
         self._open(("exact_list", "tbl_keys", "cov_delta"))
         lap("open")
-        prev, it = -1, 0
+        prev, it, grow = -1, 0, 0
         while True:
-            counts = self._gather_u32(n)
+            both = [struct.unpack("<II", b) for b in self.comm.all_gather_bytes(struct.pack("<II", n, grow))]
             lap("exchange")
+            if any(g for _, g in both):  # the table would have to grow under the replicas: serial path from T0
+                e.shard_abort()
+                stat["mode"] = "serial (table growth)"
+                return self._scan_serial(fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom, begun="records", r_begin=r0)
+            counts = [c for c, _ in both]
             total = sum(counts)
             stat["exact"].append(total)
             if total == 0 or total == prev:
                 break
             grow = e.shard_execute(counts, it)
             lap("execute")
-            grows = self._gather_u32(grow)
-            lap("exchange")
-            if any(grows):  # the table would have to grow under the replicas: serial path from T0
-                e.shard_abort()
-                stat["mode"] = "serial (table growth)"
-                return self._scan_serial(fastq, paired_ends, no_cleaning, spf, spf_geom, lpf, lpf_geom, begun="records", r_begin=r0)
-            n = e.shard_verify()
+            n = 0 if grow else e.shard_verify()  # (the next list goes to the other buffer: peers may still read this one)
             lap("verify")
             prev, it = total, it + 1
         stat["iterations"] = it

@@ -183,6 +183,8 @@ int faucet_session_stitch_batch(faucet_session* s);
  * multi-GPU job the GPU that owns a shard does it before rank 0 imports the shard.  Optional: stitch_batch sorts
  * itself when the batch comes without. */
 int faucet_session_flow_prepare(faucet_session* s);
+/* ... of the first n records only; concurrent != 0: on a second stream, next to what is queued on the session's */
+int faucet_session_flow_prepare_records(faucet_session* s, uint32_t n, int concurrent);
 int faucet_session_load_stats(faucet_session* s, faucet_load_stats* out, uint64_t total_lines);
 int faucet_session_set_profiling(faucet_session* s, int on);   /* per-kernel CUDA-event timing */
 int faucet_session_get_bloom(faucet_session* s, uint8_t* bloo2_out, uint8_t* bloo1_out);
