@@ -128,7 +128,7 @@ def survey_bytes(w, n_hash, weight2, r_contained):
     return a_load, a_scan
 
 
-SHARD_PREFIX_PCT = 60  # share of shard 0 that GPU 0 stitches in order before the sharded epoch starts
+SHARD_PREFIX_PCT = 70  # share of shard 0 that GPU 0 stitches in order before the sharded epoch starts
 L2_BYTES = 100e6  # what of the 126 MB L2 a randomly probed structure can count on
 
 

@@ -55,7 +55,9 @@ struct Global {
   bool retain_planes = false;         // pass 1 keeps the parsed planes of every batch in HBM for faucet_gpu_scan_retained
   size_t retain_budget = (size_t)64 << 30;
   unsigned long long ext_cap0 = 1ull << 24;
-  bool dry_lazy = true;               // read-only walks look junction keys up as they reach them (no parked line: 10.3 vs 13.5 ms per 1.8 M records)
+  int dry_lazy = 2;                   // read-only walks look junction keys up as they reach them instead of parking the lookups of
+                                      // the whole line first: 1 = always (10.3 vs 13.5 ms per 1.8 M records at configs[1], keys in
+                                      // L2), 0 = never, 2 = while the key array fits L2 (configs[2]: 5 GB table, 288 vs ~130 ms)
   bool shard_force_abort = false;     // tests: the first exact run of a sharded epoch reports "table must grow"
   size_t load_sub_bytes0 = (size_t)1 << 20, load_sub_bytes = (size_t)64 << 20;  // first / largest load sub-batch
   faucet_timings tim{};
@@ -397,7 +399,8 @@ int faucet_gpu_set_tuning(const char* name, uint64_t value) {
     if (value < 64) return fail(FAUCET_E_ARG, "ext_cap0 out of range");
     g.ext_cap0 = value;
   } else if (n == "dry_lazy") {
-    g.dry_lazy = value != 0;
+    if (value > 2) return fail(FAUCET_E_ARG, "dry_lazy must be 0, 1 or 2 (while the keys fit L2)");
+    g.dry_lazy = (int)value;
   } else if (n == "shard_force_abort") {
     g.shard_force_abort = value != 0;
   } else {
@@ -914,7 +917,7 @@ static void stitch_fill_args(faucet_session* s, StitchArgs& a) {
   a.w_min = std::min<uint32_t>(64, s->w_max); a.w_max = s->w_max;
   a.shrink_den = g.stitch_shrink_den; a.grow_den = g.stitch_grow_den;
   a.cov_stride = REC_WORDS; a.cov_off = REC_COV;
-  a.lazy = g.dry_lazy ? 1 : 0;
+  a.lazy = g.dry_lazy == 1 || (g.dry_lazy == 2 && (s->tbl_cap + 1) * 8 <= ((size_t)64 << 20)) ? 1 : 0;
 }
 
 // moves what the kernels left in the extension-list buffer to the host

@@ -731,7 +731,12 @@ __device__ bool dry_forward(const StitchArgs& a, WarpCtx& c, uint32_t s0, int le
   while (true) {
     bool found = false;
     int slot = -1;
-    while (tp < tested_end) {
+    if (LAZY && have_last && tp < tested_end) {  // after a skip the cursor normally stands on the next known junction: one probe
+      const uint64_t fwd = line_kmer(a, c, rel + (tp >> 1));
+      slot = tbl_find(a, (tp & 1) ? fwd : revcomp(fwd, k));
+      found = slot >= 0;
+    }
+    while (!found && tp < tested_end) {
       const int t = tp + lane;
       const bool active = t < tested_end;
       bool known = false, spc = false, tst = false;

@@ -64,7 +64,7 @@ PLANES = ("inval", "packed", "flags", "seq_start", "seq_end")
 
 
 class ShardedJob:
-    def __init__(self, engine, comm, sharded_stitch=True, prefix_pct=60):
+    def __init__(self, engine, comm, sharded_stitch=True, prefix_pct=70):
         """sharded_stitch: take the sharded epoch when the scan allows it; prefix_pct: share of shard 0 that rank 0
         runs through the ordered executor before the epoch starts (the dense start of the stream)"""
         self.eng, self.comm = engine, comm

@@ -148,7 +148,8 @@ int faucet_gpu_get_timings(faucet_timings* out);
  *           adaptation; "stitch_blocks" resident CTAs per SM (2..4); "ext_cap0" u64 words of the extension-list buffer
  *           that feeds the long pair filter; "shard_force_abort" 1 = a sharded epoch's first exact run reports that the
  *           table must grow (tests of the fallback to the serial path); "dry_lazy" 1 = the read-only walks of the epochs look
- *           junction keys up as they reach them (default), 0 = they park the lookups of the whole line first
+ *           junction keys up as they reach them, 0 = they park the lookups of the whole line first, 2 = lazy while the key
+ *           array fits L2 (default)
  *  scan:    "scan_memo" 1 = scan_flags caches the extension masks of every k-mer it has computed (default), 0 = every
  *           position from the Bloom filter; "memo_shift" cache entries = Bloom bits >> memo_shift (8 bytes each)
  *  load:    "load_sub_bytes0" / "load_sub_bytes" first / largest sub-batch of pass 1; "load_memo_log2" pass 1 caches

@@ -25,14 +25,16 @@ def main():
     res = {"rank": rank, "ok": True, "msg": ""}
     try:
         # (k, j, no_cleaning, share of shard 0 that rank 0 runs in order before the sharded epoch, forced fallback)
-        for (k, j, no_cleaning, prefix_pct, force_abort) in ((31, 1, 1, 100, 0), (31, 1, 1, 30, 0), (27, 2, 1, 0, 0), (31, 1, 1, 50, 1),
-                                                            (21, 0, 0, 100, 0)):
+        # + read-only walks: 2 = lazy lookups while the keys fit L2 (here: always), 0 = parked lookups
+        for (k, j, no_cleaning, prefix_pct, force_abort, lazy) in ((31, 1, 1, 100, 0, 2), (31, 1, 1, 30, 0, 0), (27, 2, 1, 0, 0, 2),
+                                                                  (31, 1, 1, 50, 1, 2), (21, 0, 0, 100, 0, 2), (25, 1, 1, 60, 0, 2)):
             _, lt, nh = fb.geometry_from_reads(60000, 30000, 0.04)
             shards = fb.plan_shards(text, True, world)
             a, b = shards[rank]
             cap = max(y - x for x, y in shards) + 1024
             s = fb.Session(k, lt, nh, j=j, max_spacer_dist=100, max_text_bytes=cap)
             fb.set_tuning("shard_force_abort", force_abort)
+            fb.set_tuning("dry_lazy", lazy)
             job = ShardedJob(s, TorchComm(torch.device("cuda", local)), prefix_pct=prefix_pct)
             job.setup()
             o = Oracle()

@@ -42,7 +42,8 @@ def small_fa(tmp_path_factory):
                     err=0.01, nrate=0.004, fasta=True)
 
 
-EPOCH_DEFAULTS = {"epoch_mode": 0, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 22}
+EPOCH_DEFAULTS = {"epoch_mode": 0, "epoch0": 8192, "epoch_max": 1 << 20, "epoch_recheck": 1, "stitch_exec": 1, "flow_chunk": 1 << 22,
+                  "dry_lazy": 2}
 EPOCH_SCHEDULES = {
     "adaptive": {"epoch_mode": 1},                                      # ordered epochs first, then classify epochs
     "ordered_only": {},                                                 # the default: every record through the dataflow executor
@@ -52,6 +53,7 @@ EPOCH_SCHEDULES = {
     "flow_small_chunks": {"epoch_mode": 1, "epoch0": 1024, "flow_chunk": 700},  # dependency sort every 700 records
     "classify_tiny": {"epoch_mode": 2, "epoch0": 192, "epoch_max": 3000},  # classify / execute / verify / apply from record 0 on
     "classify_join": {"epoch_mode": 2, "epoch0": 500, "epoch_max": 8000, "epoch_recheck": 0},  # tainted records all join the exact set
+    "classify_parked": {"epoch_mode": 2, "epoch0": 400, "epoch_max": 6000, "dry_lazy": 0},  # read-only walks on parked lookups (big tables)
 }
 
 
