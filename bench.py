@@ -355,10 +355,16 @@ def run_ours(args, w):
             sess.load()
             sess.get_bloom(to_host=False)
             sess.scan_flags()
+            # the dependency sort of the stitch is a pure function of the text: it runs on a second stream next to the
+            # flagging (memory-bound next to instruction-bound), as pass 1 of the whole-pass entry points prepares it
+            sess.flow_prepare(n_recs_resident(), concurrent=True)
             return sess.stitch(True, True)
         job.load(True)
         job.scan(True, True, True)
         return 0
+
+    def n_recs_resident():
+        return sess.batch_info()[1]
 
     def step_resident():
         return step_from((dev.data_ptr(), n_text), True)  # D2D: the batch is already in HBM

@@ -1,4 +1,7 @@
-# usage: bash tools/exp/t2.sh N "pct pct ..." [extra bench args]
+# On an N-GPU box: gpurun --gpus N -- bash tools/shard_bench.sh N "pct pct ..." [extra bench args]
+# bench.py at N GPUs, once per listed share of shard 0 that GPU 0 stitches in order before the sharded epoch (FAUCET_SHARD=0
+# in the environment: the serial stitch on GPU 0); one summary line per run, JSON lines in gpurun_out/.
+mkdir -p gpurun_out
 N=$1; PCTS=$2; shift 2
 export FAUCET_BENCH_SKIP_EXTRAS=1
 for pct in $PCTS; do

@@ -1,3 +1,6 @@
+# On an N-GPU box (N >= 4: a shard must stay below 3 GiB of text): gpurun --gpus N -- bash tools/shard_bench_c3.sh N
+# configs[2] (64 Mbp, 50x, 100 bp, k = 27) split over the GPUs (strong scaling).
+mkdir -p gpurun_out
 export FAUCET_BENCH_SKIP_EXTRAS=1
 N=$1; shift
 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29811 bench.py --gpus $N --workload c3 --scaling strong --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/r2s_bench_c3_strong_n$N.json 2> gpurun_out/r2s_bench_c3_strong_n${N}_err.log; echo "rc=$?"
