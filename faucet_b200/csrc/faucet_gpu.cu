@@ -1193,7 +1193,7 @@ static int stitch_run_flow(faucet_session* s, const uint32_t* list, uint32_t beg
 
 static int stitch_ensure_epoch_buffers(faucet_session* s, uint32_t m) {
   int rc;
-  if (s->n_recs > s->in_exact_cap) {
+  if (!s->d_in_exact || s->n_recs > s->in_exact_cap) {  // (allocated even for an empty batch: a rank of a sharded job may hold no record)
     cudaFree(s->d_in_exact); s->d_in_exact = nullptr;
     s->in_exact_cap = (size_t)s->n_recs + s->n_recs / 4 + 1024;
     if ((rc = dmalloc(&s->d_in_exact, s->in_exact_cap))) return rc;
