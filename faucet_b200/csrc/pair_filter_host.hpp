@@ -59,7 +59,9 @@ class LongPairFilter {
       if (part == 0) first_[rec] = off; else more_[((uint64_t)rec << 16) | part] = off;
       off += 1 + cnt;
     }
-    std::vector<uint64_t> cur;
+    // Every extension takes part in up to |other list| pair tests; its canonical form and both hashes are computed once
+    // (addPair / containsPair hash the smaller canonical k-mer with seed 0 and the larger with seed 1).
+    std::vector<Ext> cur;
     for (uint32_t r = 0; r < n_recs; r++) {
       cur.clear();
       for (uint32_t part = 0;; part++) {
@@ -67,17 +69,30 @@ class LongPairFilter {
         if (part == 0) { off = first_[r]; if (off == ~0ull) break; }
         else { auto it = more_.find(((uint64_t)r << 16) | part); if (it == more_.end()) break; off = it->second; }
         const uint32_t cnt = (uint32_t)ext[off] & 0xffffu;
-        cur.insert(cur.end(), ext + off + 1, ext + off + 1 + cnt);
+        for (uint32_t i = 0; i < cnt; i++) {
+          const uint64_t x = ext[off + 1 + i];
+          Ext e;
+          e.canon = canon(x, revcomp(x, k_));
+          e.h0 = hash0(e.canon) & lpf_.mask;
+          e.h1 = hash1(e.canon) & lpf_.mask;
+          cur.push_back(e);
+        }
         if (more_.empty()) break;
       }
       const bool first_end = ((rec_base + r) & 1ull) == 0;
       if (first_end) { carry_.swap(cur); have_carry_ = true; continue; }
       if (have_carry_ && !carry_.empty() && !cur.empty()) {
-        for (uint64_t p1 : carry_) {  // src/ReadScanner.cpp:322-339
+        for (const Ext& p1 : carry_) {  // src/ReadScanner.cpp:322-339
           bool found = false;
-          for (uint64_t p2 : cur)
-            if (lpf_.contains_pair(p1, p2, k_)) { found = true; break; }
-          if (!found) lpf_.add_pair(p1, cur.front(), k_);
+          for (const Ext& p2 : cur) {
+            const bool lt = p1.canon < p2.canon;
+            if (lpf_.contains(lt ? p1.h0 : p2.h0, lt ? p2.h1 : p1.h1)) { found = true; break; }
+          }
+          if (!found) {
+            const Ext& p2 = cur.front();
+            const bool lt = p1.canon < p2.canon;
+            lpf_.add(lt ? p1.h0 : p2.h0, lt ? p2.h1 : p1.h1);
+          }
         }
       }
       have_carry_ = false;
@@ -87,7 +102,8 @@ class LongPairFilter {
  private:
   HostBloom lpf_;
   int k_ = 0;
-  std::vector<uint64_t> carry_;  // mate-1 list waiting for its mate (may span a batch boundary)
+  struct Ext { uint64_t canon, h0, h1; };  // an extension k-mer: canonical form, seed-0 and seed-1 hash (masked)
+  std::vector<Ext> carry_;       // mate-1 list waiting for its mate (may span a batch boundary)
   bool have_carry_ = false;
   std::vector<uint64_t> first_;
   std::unordered_map<uint64_t, uint64_t> more_;
