@@ -128,7 +128,8 @@ def survey_bytes(w, n_hash, weight2, r_contained):
     return a_load, a_scan
 
 
-SHARD_PREFIX_PCT = 70  # share of shard 0 that GPU 0 stitches in order before the sharded epoch starts
+# share of shard 0 that GPU 0 stitches in order before the sharded epoch starts (None: ShardedJob's default for the world size)
+SHARD_PREFIX_PCT = int(os.environ["FAUCET_SHARD_PREFIX_PCT"]) if os.environ.get("FAUCET_SHARD_PREFIX_PCT") else None
 L2_BYTES = 100e6  # what of the 126 MB L2 a randomly probed structure can count on
 
 
@@ -250,7 +251,7 @@ def sharded_parity_check(fb, torch, dist, rank, world, local):
     a, b = shards[rank]
     s = fb.Session(k, lt, nh, j=J, max_spacer_dist=MAX_SPACER, max_text_bytes=max(y - x for x, y in shards) + 1024)
     job = ShardedJob(s, TorchComm(torch.device("cuda", local)), sharded_stitch=os.environ.get("FAUCET_SHARD", "1") != "0",
-                     prefix_pct=int(os.environ.get("FAUCET_SHARD_PREFIX_PCT", str(SHARD_PREFIX_PCT))))
+                     prefix_pct=SHARD_PREFIX_PCT)
     job.setup()
     s.set_text(text[a:b])
     job.load(True)
@@ -327,7 +328,7 @@ def run_ours(args, w):
         from faucet_b200.multi import ShardedJob, TorchComm
         # FAUCET_SHARD=0: the serial stitch on GPU 0; FAUCET_SHARD_PREFIX_PCT: share of shard 0 run in order before the epoch
         job = ShardedJob(sess, TorchComm(torch.device("cuda", local)), sharded_stitch=os.environ.get("FAUCET_SHARD", "1") != "0",
-                         prefix_pct=int(os.environ.get("FAUCET_SHARD_PREFIX_PCT", str(SHARD_PREFIX_PCT))))
+                         prefix_pct=SHARD_PREFIX_PCT)
         job.setup()
 
     def step_parts(base):  # several batches through the stage API (load accumulates; one junction map)
