@@ -8,8 +8,9 @@
 //   3. the exact two-filter load of load.cuh runs on the shard, starting from that bloo1
 //   4. the per-shard bloo2 arrays are OR-all-reduced in place over NVLink  (bloom_or_allreduce_kernel;
 //      NCCL has no bitwise-OR reduction)
-// Pass 2: scan_flags shards freely (pure); the stitch is sequential by nature and runs on GPU 0, which
-// pulls the other GPUs' planes over NVLink shard by shard.
+// Pass 2: scan_flags shards freely (pure); the stitch is one sequential state -- shard.cuh shards what of it commutes
+// (the sharded epoch); the serial form (GPU 0 pulls the other GPUs' planes over NVLink shard by shard) stays as the
+// path of scans that feed the pair filters.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

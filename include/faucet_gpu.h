@@ -238,8 +238,12 @@ int faucet_session_batch_info(faucet_session* s, size_t* n_text, uint32_t* n_rec
  * the serial stitch, bit for bit (src/ReadScanner.cpp:61-231, utils/JunctionMap.cpp:533-570).
  *   every rank:  stitch_begin;  owner: stitch_records(0, r0, 0)
  *   shard_info -> all-gather -> open_peers(TBL_PACK, JSLOT) -> shard_begin -> open_peers(EXACT_LIST, TBL_KEYS, COV_DELTA)
- *   repeat { all-gather n_exact; stop when no list grew;  shard_execute; [any need_grow: shard_abort, serial path];  shard_verify }
- *   shard_finish -> all-gather stats -> owner: shard_merge (others: shard_end) */
+ *   repeat { all-gather (n_exact, need_grow) [any need_grow: shard_abort, serial path]; stop when no list grew;
+ *            shard_execute(n_exact of every rank, iteration);  shard_verify }
+ *   shard_finish -> all-gather stats -> owner: shard_merge (others: shard_end)
+ * A rank's exact-set list lives in FAUCET_BUF_EXACT_LIST, two buffers n_recs entries apart used alternately by iteration
+ * parity (a rank may write its next list while a peer still reads the current one).  stitch_records(begin, end, advance):
+ * the ordered executor over a record range of the resident batch (advance: the batch is complete, later batches follow). */
 #define FAUCET_SHARD_INFO_BYTES 512
 #define FAUCET_SHARD_STATS 32
 int faucet_session_stitch_records(faucet_session* s, uint32_t begin, uint32_t end, int advance);
